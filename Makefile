@@ -1,0 +1,46 @@
+# Build of the B200-native P3DFFT++ transform path.
+#   make            -> p3dfft.3_b200/lib/libp3dfft.3.so   (host C++ + sm_100a CUDA layer; the product)
+#   make emu        -> tools/cuda_emu/_build/libp3dfft_emu.so (CPU-thread emulation of the kernels; dev/test tool only)
+#   make samples    -> the reference's own sample programs, compiled UNMODIFIED from REFERENCE against this library
+#   make oracle     -> oracle/_build (C restatement) and, when REFERENCE exists, oracle/_ref (reference host code on shims)
+PKG      := p3dfft.3_b200
+NVCC     := nvcc
+CXX      := g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-comment -Iinclude -Iinclude/compat -I$(PKG)/host
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -I$(PKG)/csrc
+HOSTSRC  := geometry registry planner executor cwrap minimpi
+OBJDIR   := $(PKG)/lib/obj
+HOSTOBJ  := $(HOSTSRC:%=$(OBJDIR)/%.o)
+LIB      := $(PKG)/lib/libp3dfft.3.so
+EMUDIR   := tools/cuda_emu/_build
+EMULIB   := $(EMUDIR)/libp3dfft_emu.so
+CUDA_HOME ?= /usr/local/cuda
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(PKG)/host/%.cpp include/p3dfft.h include/p3dfft_b200.h include/Cwrap.h $(PKG)/host/plan.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(OBJDIR)/gpu_layer.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o
+	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static -ldl -lrt -lpthread
+
+emu: $(EMULIB)
+$(EMUDIR)/gpu_layer_emu.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
+	@mkdir -p $(EMUDIR)
+	$(CXX) -O1 -std=c++17 -fPIC -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -c $< -o $@
+$(EMUDIR)/emu_globals.o: tools/cuda_emu/emu_globals.cpp tools/cuda_emu/cuda_runtime.h
+	@mkdir -p $(EMUDIR)
+	$(CXX) -O1 -std=c++17 -fPIC -Itools/cuda_emu -c $< -o $@
+$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o
+	$(CXX) -shared -o $@ $^ -lrt -lpthread
+
+clean:
+	rm -rf $(PKG)/lib $(EMUDIR)
+
+.PHONY: all emu clean

@@ -1,0 +1,136 @@
+/* p3dfft_b200.h -- the two C ABIs that are new in the B200 build.
+ *
+ * (1) p3dfft_b200_*  : public extensions next to the reference's C API (Cwrap.h): stream control,
+ *     synchronisation, plan introspection, launch counters.  Nothing in the reference corresponds to
+ *     them; they exist because in/out may now be device pointers.
+ * (2) p3dfftcu_*     : the thin GPU layer the C++ host code calls.  It replaces, one for one, the places
+ *     where the reference calls into FFTW and MPI on its hot path:
+ *       - fftw[f]_plan_many_dft[_r2c|_c2r] / fftw[f]_plan_many_r2r   (build/templ.C:1283-1366,
+ *         build/init.C:1191-1607)                                  -> p3dfftcu_stage_create
+ *       - fftw[f]_execute_dft[_r2c|_c2r] / fftw[f]_execute_r2r       (build/init.C:1146-1188) fused with
+ *         transplan::reorder_trans / reorder_deriv / reorder_out     (build/exec.C:737-2032) and
+ *         pack_sendbuf_trans + MPI_Alltoallv + unpack_recvbuf        (build/exec.C:2358-2957, :2698)
+ *                                                                    -> p3dfftcu_stage_exec
+ *       - compute_deriv<T>                                           (build/deriv.C:85-185)
+ *                                                                    -> p3dfftcu_deriv
+ *     Plain pointers and sizes only; host code never includes CUDA headers.
+ * All p3dfftcu_* functions return 0 on success, non-zero on error (message via p3dfftcu_last_error()).
+ */
+#ifndef P3DFFT_B200_ABI_H
+#define P3DFFT_B200_ABI_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- public extensions */
+const char *p3dfft_b200_version(void);
+/* CUDA stream (cudaStream_t) every later exec call is enqueued on; NULL = legacy default stream */
+void p3dfft_b200_set_stream(void *cuda_stream);
+/* wait until all work enqueued by exec calls with device pointers has finished */
+void p3dfft_b200_sync(void);
+/* number of kernels this library has launched since load (stage kernels, copies excluded) */
+long long p3dfft_b200_kernel_launches(void);
+/* JSON description of a 3D plan (stages, layouts, exchange segments); returns bytes needed */
+size_t p3dfft_b200_describe_plan3d(int plan, char *buf, size_t buflen);
+size_t p3dfft_b200_describe_plan1d(int plan, char *buf, size_t buflen);
+/* per-stage CUDA-event timing: 1 = on.  Read back with p3dfft_b200_stage_times (ms of the last exec) */
+void p3dfft_b200_enable_timers(int on);
+int p3dfft_b200_stage_times(int plan, float *ms, int max_stages);
+/* 1 if a usable CUDA device was found at p3dfft_setup() (plans can be built and inspected without one) */
+int p3dfft_b200_have_device(void);
+
+/* ---------------------------------------------------------------- thin GPU layer */
+enum {
+  P3DFFTCU_K_EMPTY = 0,   /* copy / reorder / pack only */
+  P3DFFTCU_K_C2C_FWD = 1, /* Y_k = sum x_j exp(-2 pi i jk/N)      (FFTW_FORWARD)  */
+  P3DFFTCU_K_C2C_BWD = 2, /* Y_k = sum x_j exp(+2 pi i jk/N)      (FFTW_BACKWARD) */
+  P3DFFTCU_K_R2C = 3,     /* real N -> complex N/2+1 */
+  P3DFFTCU_K_C2R = 4,     /* complex N/2+1 -> real N, unnormalised */
+  P3DFFTCU_K_DCT1 = 5,    /* FFTW_REDFT00 */
+  P3DFFTCU_K_DST1 = 6,    /* FFTW_RODFT00 */
+  P3DFFTCU_K_DCT2 = 7,    /* FFTW_REDFT10 */
+  P3DFFTCU_K_DST2 = 8,    /* FFTW_RODFT10 */
+  P3DFFTCU_K_DCT3 = 9,    /* FFTW_REDFT01 */
+  P3DFFTCU_K_DST3 = 10,   /* FFTW_RODFT01 */
+  P3DFFTCU_K_DCT4 = 11,   /* FFTW_REDFT11 */
+  P3DFFTCU_K_DST4 = 12    /* FFTW_RODFT11 */
+};
+
+#define P3DFFTCU_MAXSEG 32
+
+/* Where the outputs k in [k0,k1) of every pencil go: element (k,u,v) is written to
+ * dst[slot] + (off + (k-k0)*os_d + u*os_u + v*os_v) elements.  One segment per exchange peer
+ * (slot selects that peer's buffer); a purely local stage has a single segment. */
+typedef struct p3dfftcu_seg {
+  int k0, k1;
+  int slot;
+  int pad_;
+  long long off, os_d, os_u, os_v;
+} p3dfftcu_seg;
+
+/* One stage = batched 1D transform of nu*nv pencils along dimension d, read with strides is_*,
+ * written through the segment table.  Strides are in elements of the respective data type. */
+typedef struct p3dfftcu_stage_desc {
+  int kind;          /* P3DFFTCU_K_* */
+  int prec;          /* 4 or 8 */
+  int dt_in, dt_out; /* 1 real, 2 complex (interleaved) */
+  int nfft;          /* logical transform length (FFTW's n) */
+  int n_in, n_out;   /* elements per pencil read / written */
+  int nseg;
+  long long nu, nv;
+  long long is_d, is_u, is_v;
+  p3dfftcu_seg seg[P3DFFTCU_MAXSEG];
+} p3dfftcu_stage_desc;
+
+typedef struct p3dfftcu_stage_s *p3dfftcu_stage;
+
+const char *p3dfftcu_last_error(void);
+int p3dfftcu_device_count(void);
+/* bind this process to a device; device < 0 picks LOCAL_RANK (or P3DFFT_RANK) modulo device count */
+int p3dfftcu_init(int device);
+int p3dfftcu_malloc(void **ptr, size_t bytes);
+int p3dfftcu_free(void *ptr);
+int p3dfftcu_memset(void *ptr, int value, size_t bytes, void *stream);
+/* kind: 0 host->device, 1 device->host, 2 device->device; asynchronous on `stream` */
+int p3dfftcu_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream);
+int p3dfftcu_stream_sync(void *stream);
+/* 1 device memory, 0 host memory (pageable or pinned), <0 error */
+int p3dfftcu_pointer_is_device(const void *ptr);
+
+int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out);
+int p3dfftcu_stage_destroy(p3dfftcu_stage st);
+/* deriv_g > 0: multiply output k by i*k (k<g/2), 0 (k==g/2), i*(k-g) (k>g/2)  (exec.C:228-287) */
+int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream);
+/* human-readable name of the kernel variant picked for this stage */
+const char *p3dfftcu_stage_variant(p3dfftcu_stage st);
+
+/* out = i*kappa*in along storage dimension ldir of a complex array with storage extents sd[3];
+ * kappa from global index gstart+local index and full length g (deriv.C:85-185) */
+int p3dfftcu_deriv(const void *in, void *out, int prec, const int sd[3], int ldir, int g, int gstart, void *stream);
+
+/* events (per-stage timers) */
+int p3dfftcu_event_create(void **ev);
+int p3dfftcu_event_destroy(void *ev);
+int p3dfftcu_event_record(void *ev, void *stream);
+int p3dfftcu_event_elapsed(void *ev0, void *ev1, float *ms);
+
+/* peer memory for the fused exchange: export a cudaMalloc'd buffer, open a peer's export */
+#define P3DFFTCU_IPC_BYTES 64
+int p3dfftcu_ipc_export(void *ptr, char handle[P3DFFTCU_IPC_BYTES]);
+int p3dfftcu_ipc_open(const char handle[P3DFFTCU_IPC_BYTES], void **ptr);
+int p3dfftcu_ipc_close(void *ptr);
+/* stream-ordered barrier among n peers (self included or not): writes `epoch` into word `my_slot` of every
+ * peer_flags[j] array, then waits until words peer_slots[j] of my_flags all reach `epoch`.  Flag arrays are
+ * 8-byte words, zero-initialised, one word per world rank; epochs must increase from call to call. */
+int p3dfftcu_peer_barrier(void *const *peer_flags, const int *peer_slots, int n, void *my_flags, int my_slot,
+                          unsigned long long epoch, void *stream);
+
+long long p3dfftcu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

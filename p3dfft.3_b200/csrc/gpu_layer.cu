@@ -1,0 +1,475 @@
+// gpu_layer.cu -- implementation of the p3dfftcu_* C ABI (include/p3dfft_b200.h): device selection,
+// memory, twiddle tables, stage planning (kernel variant + tile shape) and launch, stand-alone
+// spectral derivative, CUDA-IPC peer mapping and the stream-ordered peer barrier.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "generic_stage.cuh"
+#include "pow2_stage.cuh"
+
+using namespace p3b;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+int g_device = -1;
+int g_num_sms = 148;
+size_t g_smem_optin = 227 * 1024;
+
+int fail(const char *what, cudaError_t e) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 1;
+}
+int failmsg(const std::string &m) {
+  g_err = m;
+  return 1;
+}
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return fail(#call, e__); \
+  } while (0)
+
+// ------------------------------------------------------------------ twiddle tables
+// which: 0 -> exp(-2 pi i j/n), j<n;  1 -> exp(-i pi j/(2n)), j<2n;  2 -> exp(-i pi (2j+1)/(4n)), j<n
+std::mutex g_tw_mu;
+std::map<std::tuple<int, int, int>, void *> g_tw;
+
+template <typename T> int build_table(int which, int n, void **out) {
+  int len = which == 1 ? 2 * n : n;
+  std::vector<T> h(2 * (size_t)len);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int j = 0; j < len; j++) {
+    long double a;
+    if (which == 0) a = -2.0L * pi * (long double)j / (long double)n;
+    else if (which == 1) a = -pi * (long double)j / (2.0L * (long double)n);
+    else a = -pi * (long double)(2 * j + 1) / (4.0L * (long double)n);
+    h[2 * j] = (T)cosl(a);
+    h[2 * j + 1] = (T)sinl(a);
+  }
+  void *d = nullptr;
+  CK(cudaMalloc(&d, h.size() * sizeof(T)));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+int get_table(int which, int n, int prec, const void **out) {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(which, n, prec);
+  auto it = g_tw.find(key);
+  if (it != g_tw.end()) {
+    *out = it->second;
+    return 0;
+  }
+  void *d = nullptr;
+  int rc = prec == 8 ? build_table<double>(which, n, &d) : build_table<float>(which, n, &d);
+  if (rc) return rc;
+  g_tw[key] = d;
+  *out = d;
+  return 0;
+}
+
+// ------------------------------------------------------------------ deriv + barrier kernels
+struct DerivParams {
+  const void *in;
+  void *out;
+  long long total;
+  int sd0, sd1, ldir, g, gstart;
+};
+
+template <typename T> __global__ void deriv_kernel(const __grid_constant__ DerivParams p) {
+  typedef typename cx<T>::type C;
+  const C *in = (const C *)p.in;
+  C *out = (C *)p.out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (long long)gridDim.x * blockDim.x) {
+    int c;
+    if (p.ldir == 0) c = (int)(i % p.sd0);
+    else if (p.ldir == 1) c = (int)((i / p.sd0) % p.sd1);
+    else c = (int)(i / ((long long)p.sd0 * p.sd1));
+    T kap = (T)deriv_kappa(c + p.gstart, p.g);
+    C x = in[i];
+    out[i] = mk<T>(-kap * x.y, kap * x.x);
+  }
+}
+
+struct BarrierParams {
+  unsigned long long *peer[64];
+  int slot[64];
+  unsigned long long *mine;
+  int n, my_slot;
+  unsigned long long epoch;
+};
+
+#ifndef P3B_EMU
+__global__ void peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
+  int j = threadIdx.x;
+  if (j >= p.n) return;
+  __threadfence_system();
+  unsigned long long *remote = p.peer[j] + p.my_slot;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(p.epoch) : "memory");
+  const unsigned long long *mine = p.mine + p.slot[j];
+  unsigned long long t0, t1, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= p.epoch) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 30000000000ull) {  // 30 s: a peer died; fail loudly instead of hanging the GPU
+      printf("p3dfft_b200: peer barrier timed out (slot %d waiting for slot %d, epoch %llu, seen %llu)\n", p.my_slot,
+             p.slot[j], p.epoch, v);
+      __trap();
+    }
+    __nanosleep(200);
+  }
+}
+#endif
+
+// ------------------------------------------------------------------ stage object
+enum Variant { V_GENERIC = 0, V_POW2 = 1 };
+
+}  // namespace
+
+struct p3dfftcu_stage_s {
+  p3dfftcu_stage_desc d;
+  StageParams P;
+  Variant variant;
+  int threads;
+  int grid;
+  size_t smem;
+  Pow2Plan pw;
+  std::string name;
+};
+
+namespace {
+
+void factorize(int L, int *fac, int *nfac) {
+  int n = 0;
+  while (L % 4 == 0) { fac[n++] = 4; L /= 4; }
+  while (L % 2 == 0) { fac[n++] = 2; L /= 2; }
+  for (int p = 3; (long long)p * p <= L; p += 2)
+    while (L % p == 0) { fac[n++] = p; L /= p; }
+  if (L > 1) fac[n++] = L;
+  *nfac = n;
+}
+
+int internal_length(int kind, int n) {
+  switch (kind) {
+    case P3DFFTCU_K_DCT1: return 2 * (n - 1);
+    case P3DFFTCU_K_DST1: return 2 * (n + 1);
+    case P3DFFTCU_K_DCT2: case P3DFFTCU_K_DST2: case P3DFFTCU_K_DCT3: case P3DFFTCU_K_DST3:
+    case P3DFFTCU_K_DCT4: case P3DFFTCU_K_DST4: return 2 * n;
+    default: return n;
+  }
+}
+
+// which of (d,u,v) is the unit-stride direction: 0 d, 1 u, 2 v
+int fastest(long long sd, long long su, long long sv, long long nd, long long nu, long long nv) {
+  long long best = -1;
+  int which = 0;
+  long long s[3] = {sd, su, sv}, n[3] = {nd, nu, nv};
+  for (int i = 0; i < 3; i++) {
+    if (n[i] <= 1) continue;
+    if (best < 0 || s[i] < best) { best = s[i]; which = i; }
+  }
+  return which;
+}
+
+template <typename T> int setup_generic(p3dfftcu_stage_s *st) {
+  const p3dfftcu_stage_desc &d = st->d;
+  StageParams &P = st->P;
+  size_t csz = 2 * sizeof(T);
+  P.lstride = P.L + 1;
+  size_t per_pencil = 2 * (size_t)P.lstride * csz;
+  size_t budget = g_smem_optin - 1024;
+  int pmax = (int)(budget / per_pencil);
+  if (pmax < 1) return failmsg("transform length too large for the shared-memory stage kernel");
+  int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
+  int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
+  int run = (int)(128 / csz);  // pencils per tile for 128-byte runs across pencils
+  if (run < 4) run = 4;
+  int tu = 1, tv = 1;
+  auto clampll = [](long long a, long long b) { return (int)(a < b ? a : b); };
+  bool needU = (fin == 1 || fout == 1), needV = (fin == 2 || fout == 2);
+  if (needU && needV) {
+    int side = 1;
+    while ((side + 1) * (side + 1) <= pmax && side + 1 <= 8) side++;
+    tu = clampll(side, d.nu);
+    tv = clampll(pmax / tu > 8 ? 8 : pmax / tu, d.nv);
+  } else if (needU) {
+    tu = clampll(pmax < run ? pmax : run, d.nu);
+  } else if (needV) {
+    tv = clampll(pmax < run ? pmax : run, d.nv);
+  } else {
+    int want = 4096 / (P.L > 0 ? P.L : 1);
+    if (want < 1) want = 1;
+    if (want > pmax) want = pmax;
+    tu = clampll(want, d.nu);
+    tv = clampll(want / tu > 0 ? want / tu : 1, d.nv);
+  }
+  P.tile_u = tu;
+  P.tile_v = tv;
+  P.load_ord = fin == 0 ? ORD_D : (fin == 1 ? ORD_U : ORD_V);
+  P.store_ord = fout == 0 ? ORD_D : (fout == 1 ? ORD_U : ORD_V);
+  P.tiles_u = (d.nu + tu - 1) / tu;
+  P.ntiles = P.tiles_u * ((d.nv + tv - 1) / tv);
+  st->threads = 256;
+  st->smem = (size_t)tu * tv * per_pencil;
+  auto kern = generic_stage_kernel<T>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem_optin));
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, st->threads, st->smem));
+  if (occ < 1) occ = 1;
+  long long g = (long long)g_num_sms * occ;
+  st->grid = (int)(P.ntiles < g ? P.ntiles : g);
+  if (st->grid < 1) st->grid = 1;
+  char nm[160];
+  snprintf(nm, sizeof nm, "generic<%s> L=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d", sizeof(T) == 8 ? "f64" : "f32",
+           P.L, tu, tv, P.load_ord, P.store_ord, st->smem, st->grid);
+  st->name = nm;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *p3dfftcu_last_error(void) { return g_err.c_str(); }
+
+int p3dfftcu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int p3dfftcu_init(int device) {
+  int n = p3dfftcu_device_count();
+  if (n <= 0) return failmsg("no CUDA device available");
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    if (!lr) lr = getenv("P3DFFT_RANK");
+    device = lr ? atoi(lr) % n : 0;
+    int cur = 0;
+    if (!lr && cudaGetDevice(&cur) == cudaSuccess) device = cur;
+  }
+  CK(cudaSetDevice(device));
+  g_device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  g_num_sms = prop.multiProcessorCount;
+  g_smem_optin = prop.sharedMemPerBlockOptin;
+  if (prop.major < 10) {
+    char m[200];
+    snprintf(m, sizeof m, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a code only",
+             device, prop.name, prop.major, prop.minor);
+    return failmsg(m);
+  }
+  return 0;
+}
+
+int p3dfftcu_malloc(void **ptr, size_t bytes) {
+  CK(cudaMalloc(ptr, bytes ? bytes : 16));
+  return 0;
+}
+int p3dfftcu_free(void *ptr) {
+  if (ptr) CK(cudaFree(ptr));
+  return 0;
+}
+int p3dfftcu_memset(void *ptr, int value, size_t bytes, void *stream) {
+  CK(cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream));
+  return 0;
+}
+int p3dfftcu_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream) {
+  cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  CK(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+  return 0;
+}
+int p3dfftcu_stream_sync(void *stream) {
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+int p3dfftcu_pointer_is_device(const void *ptr) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) {
+  const p3dfftcu_stage_desc &d = *desc;
+  if (d.prec != 4 && d.prec != 8) return failmsg("stage: prec must be 4 or 8");
+  if (d.nseg < 1 || d.nseg > P3DFFTCU_MAXSEG) return failmsg("stage: bad segment count");
+  if (d.kind < 0 || d.kind > P3DFFTCU_K_DST4) return failmsg("stage: unknown kind");
+  if (d.nfft < 1) return failmsg("stage: transform length must be positive");
+  if (d.kind == P3DFFTCU_K_DCT1 && d.nfft < 2) return failmsg("stage: DCT-I needs n >= 2");
+  p3dfftcu_stage_s *st = new p3dfftcu_stage_s();
+  st->d = d;
+  StageParams &P = st->P;
+  memset(&P, 0, sizeof P);
+  P.nu = d.nu; P.nv = d.nv; P.is_d = d.is_d; P.is_u = d.is_u; P.is_v = d.is_v;
+  P.kind = d.kind; P.dt_in = d.dt_in; P.dt_out = d.dt_out;
+  P.nfft = d.nfft; P.n_in = d.n_in; P.n_out = d.n_out;
+  P.L = internal_length(d.kind, d.nfft);
+  P.nseg = d.nseg;
+  for (int s = 0; s < d.nseg; s++) {
+    P.seg[s].k0 = d.seg[s].k0; P.seg[s].k1 = d.seg[s].k1;
+    P.seg[s].off = d.seg[s].off; P.seg[s].os_d = d.seg[s].os_d; P.seg[s].os_u = d.seg[s].os_u; P.seg[s].os_v = d.seg[s].os_v;
+    P.seg[s].base = nullptr;
+  }
+  int rc = 0;
+  if (d.kind != P3DFFTCU_K_EMPTY) {
+    factorize(P.L, P.fac, &P.nfac);
+    rc = get_table(0, P.L, d.prec, &P.tw);
+    if (!rc && d.kind >= P3DFFTCU_K_DCT2) rc = get_table(1, d.nfft, d.prec, &P.tw2);
+    if (!rc && d.kind >= P3DFFTCU_K_DCT4) rc = get_table(2, d.nfft, d.prec, &P.tw3);
+  }
+  st->variant = V_GENERIC;
+  if (!rc) {
+    const char *force = getenv("P3DFFT_B200_FORCE_GENERIC");
+    bool allow_fast = !(force && atoi(force));
+    if (allow_fast && pow2_supported(d)) {
+      rc = pow2_setup(d, g_num_sms, g_smem_optin, &st->pw, &st->name);
+      if (!rc) st->variant = V_POW2;
+      else if (rc < 0) rc = 0;  // negative: not applicable, fall through to the generic kernel
+    }
+    if (!rc && st->variant == V_GENERIC) rc = d.prec == 8 ? setup_generic<double>(st) : setup_generic<float>(st);
+  }
+  if (rc) {
+    delete st;
+    return rc;
+  }
+  *out = st;
+  return 0;
+}
+
+int p3dfftcu_stage_destroy(p3dfftcu_stage st) {
+  delete st;
+  return 0;
+}
+
+const char *p3dfftcu_stage_variant(p3dfftcu_stage st) { return st->name.c_str(); }
+
+int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream) {
+  if (deriv_g > 0 && st->d.dt_out != 2) return failmsg("stage: spectral derivative needs complex output");
+  StageParams P = st->P;
+  P.in = in;
+  P.deriv_g = deriv_g;
+  for (int s = 0; s < P.nseg; s++) {
+    int slot = st->d.seg[s].slot;
+    if (slot < 0 || slot >= ndst || !dst[slot]) return failmsg("stage: missing destination buffer for a segment");
+    P.seg[s].base = dst[slot];
+  }
+  if (P.ntiles == 0 && st->variant == V_GENERIC) return 0;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (st->variant == V_POW2) {
+    int rc = pow2_launch(st->pw, P, cs);
+    if (rc) return failmsg(std::string("pow2 stage launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  } else if (st->d.prec == 8) {
+    P3B_LAUNCH(generic_stage_kernel<double>, st->grid, st->threads, st->smem, cs, P);
+  } else {
+    P3B_LAUNCH(generic_stage_kernel<float>, st->grid, st->threads, st->smem, cs, P);
+  }
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int p3dfftcu_deriv(const void *in, void *out, int prec, const int sd[3], int ldir, int g, int gstart, void *stream) {
+  long long total = (long long)sd[0] * sd[1] * sd[2];
+  if (total == 0) return 0;
+  int threads = 256;
+  long long want = (total + threads - 1) / threads;
+  int grid = (int)(want < (long long)g_num_sms * 16 ? want : (long long)g_num_sms * 16);
+  DerivParams p = {in, out, total, sd[0], sd[1], ldir, g, gstart};
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (prec == 8) P3B_LAUNCH(deriv_kernel<double>, grid, threads, 0, cs, p);
+  else P3B_LAUNCH(deriv_kernel<float>, grid, threads, 0, cs, p);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int p3dfftcu_event_create(void **ev) {
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  *ev = e;
+  return 0;
+}
+int p3dfftcu_event_destroy(void *ev) {
+  CK(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+int p3dfftcu_event_record(void *ev, void *stream) {
+  CK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream));
+  return 0;
+}
+int p3dfftcu_event_elapsed(void *ev0, void *ev1, float *ms) {
+  CK(cudaEventSynchronize((cudaEvent_t)ev1));
+  CK(cudaEventElapsedTime(ms, (cudaEvent_t)ev0, (cudaEvent_t)ev1));
+  return 0;
+}
+
+int p3dfftcu_ipc_export(void *ptr, char handle[P3DFFTCU_IPC_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) <= P3DFFTCU_IPC_BYTES, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ptr));
+  memset(handle, 0, P3DFFTCU_IPC_BYTES);
+  memcpy(handle, &h, sizeof h);
+  return 0;
+}
+int p3dfftcu_ipc_open(const char handle[P3DFFTCU_IPC_BYTES], void **ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int p3dfftcu_ipc_close(void *ptr) {
+  CK(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int p3dfftcu_peer_barrier(void *const *peer_flags, const int *peer_slots, int n, void *my_flags, int my_slot,
+                          unsigned long long epoch, void *stream) {
+  if (n > 64) return failmsg("peer barrier: too many peers");
+  BarrierParams p;
+  memset(&p, 0, sizeof p);
+  for (int j = 0; j < n; j++) {
+    p.peer[j] = (unsigned long long *)peer_flags[j];
+    p.slot[j] = peer_slots[j];
+  }
+  p.mine = (unsigned long long *)my_flags;
+  p.n = n;
+  p.my_slot = my_slot;
+  p.epoch = epoch;
+#ifndef P3B_EMU
+  peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(p);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+#else
+  (void)stream;
+  return failmsg("peer barrier is not available in the CPU emulation build");
+#endif
+}
+
+long long p3dfftcu_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// plan.h -- internal host-side representation of a planned 3D (or 1D) transform.
+// A Plan is a list of stages; a stage is one launch of a fused stage kernel (1D transform along one
+// locally-held dimension + storage reorder + optional exchange).  Replaces the reference's
+// stage / transplan / MPIplan / trans_MPIplan class family (include/p3dfft.h:529-650).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "p3dfft.h"
+
+namespace p3dfft {
+namespace b200 {
+
+// storage layout of a local 3D block: extent and element stride of each LOGICAL dimension
+struct Layout {
+  int ldims[3];
+  int mo[3];  // MemOrder: storage rank of logical dim i
+  long long stride[3];
+  long long count() const { return (long long)ldims[0] * ldims[1] * ldims[2]; }
+  void set(const int ld[3], const int mo_[3]);
+};
+
+struct PeerSeg {
+  int peer_world;  // rank in the global communicator that owns the destination
+  int peer_sub;    // its index in the exchange sub-communicator
+  int k0, k1;      // range of the transform-dimension output index it receives
+  Layout lay;      // layout of the receiver's array
+  int b_off;       // where my block starts along the gathered dimension in the receiver's array
+};
+
+struct StagePlan {
+  int kind;             // P3DFFTCU_K_*
+  int ref_kind;         // TRANS_ONLY / MPI_ONLY / TRANSMPI (reporting)
+  int dim;              // logical transform (pencil) dimension d
+  int u, v;             // the two other logical dimensions
+  int dt_in, dt_out;
+  int nfft, n_in, n_out;
+  Layout in;            // layout of the input block on this rank
+  Layout out;           // layout of the output block on this rank (exchange: what this rank RECEIVES)
+  bool exchange;
+  int xdim_gather;      // logical dim that becomes local (b); valid if exchange
+  int comm_dim;         // processor-grid dimension of the sub-communicator
+  std::vector<PeerSeg> peers;
+  p3dfftcu_stage_desc desc;
+  p3dfftcu_stage handle;
+  long long out_bytes;  // bytes of this rank's output block
+  long long in_bytes;
+  StagePlan() : handle(nullptr) {}
+};
+
+struct Plan {
+  bool ok;
+  int prec;
+  int dt_in, dt_out;
+  int nranks, rank;
+  MPI_Comm comm;
+  DataGrid *g1, *g2;
+  ProcGrid *pgrid;
+  std::vector<StagePlan> stages;
+  std::string error;
+  long long in_bytes, out_bytes;  // user-visible array sizes on this rank
+  long long work_bytes;           // per work buffer, max over stages and ranks
+  std::vector<float> stage_ms;
+  // device staging for host-pointer calls
+  void *dev_in, *dev_out;
+  long long dev_in_bytes, dev_out_bytes;
+  Plan();
+  ~Plan();
+};
+
+std::string describe(const Plan &p);
+
+// global device workspace shared by all plans: two ping-pong buffers, peer-mapped for the exchange
+struct Workspace {
+  void *buf[2];
+  long long bytes;
+  std::vector<void *> peer_buf[2];  // [which][world rank] mapped pointers (own rank = local pointer)
+  void *flags;                       // this rank's barrier flag array
+  std::vector<void *> peer_flags;    // [world rank]
+  unsigned long long epoch;
+  int nranks;
+  Workspace() : bytes(0), flags(nullptr), epoch(0), nranks(0) { buf[0] = buf[1] = nullptr; }
+};
+Workspace &workspace();
+// collective over comm: make the workspace at least `bytes` per buffer on every rank
+bool workspace_reserve(long long bytes, MPI_Comm comm, int nranks, int rank, std::string *err);
+void workspace_release();
+
+bool gpu_ready();
+void *current_stream();
+
+}  // namespace b200
+}  // namespace p3dfft
