@@ -296,6 +296,7 @@ size_t p3dfft_b200_describe_plan1d(int plan, char *buf, size_t buflen) {
 void p3dfft_b200_enable_timers(int on) { b200::set_timers(on != 0); }
 int p3dfft_b200_stage_times(int plan, float *ms, int max_stages) {
   if (plan < 0 || plan >= (int)stored_trans3D.size() || !stored_trans3D[plan]->impl) return 0;
+  b200::plan_collect_times(stored_trans3D[plan]->impl);
   const std::vector<float> &t = stored_trans3D[plan]->impl->stage_ms;
   int n = (int)t.size() < max_stages ? (int)t.size() : max_stages;
   for (int i = 0; i < n; i++) ms[i] = t[i];

@@ -189,10 +189,13 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
   }
   const size_t S = pl->stages.size();
   const bool timing = timers_on();
-  std::vector<void *> ev;
+  std::vector<void *> &ev = pl->events;
   if (timing) {
-    ev.resize(S + 1);
-    for (size_t i = 0; i <= S; i++) GPU(p3dfftcu_event_create(&ev[i]), pl, "event");
+    while (ev.size() < S + 1) {
+      void *e = nullptr;
+      GPU(p3dfftcu_event_create(&e), pl, "event");
+      ev.push_back(e);
+    }
     GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
   }
   int deriv_stage = -1;
@@ -232,15 +235,21 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
   } else if (!in_dev) {
     GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");  // the host input may be reused by the caller
   }
-  if (timing) {
-    for (size_t s = 0; s < S; s++) {
-      float ms = 0;
-      GPU(p3dfftcu_event_elapsed(ev[s], ev[s + 1], &ms), pl, "event");
-      pl->stage_ms[s] = ms;
-      add_timer(pl->stages[s], (int)s == deriv_stage, ms * 1e-3);
-    }
-    for (size_t i = 0; i <= S; i++) p3dfftcu_event_destroy(ev[i]);
+  pl->events_valid = timing;
+  pl->last_deriv_stage = deriv_stage;
+}
+
+// per-stage milliseconds of the most recent exec (waits for it to finish); also feeds p3dfft::timers
+void plan_collect_times(Plan *pl) {
+  if (!pl->events_valid) return;
+  const size_t S = pl->stages.size();
+  for (size_t s = 0; s < S; s++) {
+    float ms = 0;
+    GPU(p3dfftcu_event_elapsed(pl->events[s], pl->events[s + 1], &ms), pl, "event");
+    pl->stage_ms[s] = ms;
+    add_timer(pl->stages[s], (int)s == pl->last_deriv_stage, ms * 1e-3);
   }
+  pl->events_valid = false;
 }
 
 }  // namespace b200

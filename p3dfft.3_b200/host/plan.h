@@ -61,6 +61,9 @@ struct Plan {
   long long in_bytes, out_bytes;  // user-visible array sizes on this rank
   long long work_bytes;           // per work buffer, max over stages and ranks
   std::vector<float> stage_ms;
+  std::vector<void *> events;  // S+1 CUDA events recorded around the stages when timers are on
+  bool events_valid;
+  int last_deriv_stage;
   // device staging for host-pointer calls
   void *dev_in, *dev_out;
   long long dev_in_bytes, dev_out_bytes;
@@ -69,6 +72,7 @@ struct Plan {
 };
 
 std::string describe(const Plan &p);
+void plan_collect_times(Plan *p);
 
 // global device workspace shared by all plans: two ping-pong buffers, peer-mapped for the exchange
 struct Workspace {

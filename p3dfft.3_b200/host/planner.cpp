@@ -357,11 +357,12 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
 
 Plan::Plan()
     : ok(false), prec(0), dt_in(0), dt_out(0), nranks(1), rank(0), comm(MPI_COMM_NULL), g1(nullptr), g2(nullptr), pgrid(nullptr),
-      in_bytes(0), out_bytes(0), work_bytes(0), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0) {}
+      in_bytes(0), out_bytes(0), work_bytes(0), events_valid(false), last_deriv_stage(-1), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0) {}
 
 Plan::~Plan() {
   for (size_t s = 0; s < stages.size(); s++)
     if (stages[s].handle) p3dfftcu_stage_destroy(stages[s].handle);
+  for (size_t i = 0; i < events.size(); i++) p3dfftcu_event_destroy(events[i]);
   if (dev_in) p3dfftcu_free(dev_in);
   if (dev_out) p3dfftcu_free(dev_out);
   delete g1;

@@ -79,13 +79,21 @@ void setup() {
   REG_R2R(DST2, P3DFFTCU_K_DST2, "Sine transform DST-II")
   REG_R2R(DCT3, P3DFFTCU_K_DCT3, "Cosine transform DCT-III")
   REG_R2R(DST3, P3DFFTCU_K_DST3, "Sine transform DST-III")
-  REG_R2R(DCT4, P3DFFTCU_K_DCT4, "Cosine transform DCT-IV")
+  // The reference registers its four DCT4 IDs with the DCT-I planner (build/init.C:640,652,664,676), so a
+  // program asking for "DCT4" there gets FFTW_REDFT00.  Reproduced by default so results stay identical;
+  // P3DFFT_B200_TRUE_DCT4=1 selects the real DCT-IV (FFTW_REDFT11) kernel instead.
+  {
+    const char *e = getenv("P3DFFT_B200_TRUE_DCT4");
+    const int k4 = (e && atoi(e)) ? P3DFFTCU_K_DCT4 : P3DFFTCU_K_DCT1;
+    REG_R2R(DCT4, k4, "Cosine transform DCT-IV")
+  }
   REG_R2R(DST4, P3DFFTCU_K_DST4, "Sine transform DST-IV")
 #undef REG_R2R
 
   // bind the device.  A host without a GPU can still build and inspect plans; exec will abort.
   b200::g_gpu_ready = false;
-  if (p3dfftcu_device_count() > 0) {
+  const char *plan_only = getenv("P3DFFT_B200_PLAN_ONLY");  // build and describe plans without touching a device
+  if (!(plan_only && atoi(plan_only)) && p3dfftcu_device_count() > 0) {
     if (p3dfftcu_init(-1) == 0) b200::g_gpu_ready = true;
     else fprintf(stderr, "p3dfft_b200: %s\n", p3dfftcu_last_error());
   }
@@ -156,6 +164,8 @@ void timer::init() {
 }
 
 void timer::print(MPI_Comm comm) {
+  for (size_t i = 0; i < stored_trans3D.size(); i++)
+    if (stored_trans3D[i]->impl) b200::plan_collect_times(stored_trans3D[i]->impl);
   int rank, n;
   MPI_Comm_rank(comm, &rank);
   MPI_Comm_size(comm, &n);

@@ -1,0 +1,181 @@
+"""Kernel + planner + executor parity against the oracle, run on the CPU-thread emulation build.
+
+The emulation build (tools/cuda_emu) compiles the SAME kernel sources with g++ and runs one OS thread per
+CUDA thread; it is a development tool that lets index arithmetic be checked without a GPU.  The product
+library is exercised by tests/test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
+from util import TOL, run_1d, run_3d
+
+
+@pytest.mark.parametrize("n", [(16, 12, 10), (8, 9, 7), (6, 5, 4), (30, 3, 14)])
+def test_r2c_c2r_generic(emu, orc, n):
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+    assert run_3d(emu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
+
+
+@pytest.mark.parametrize("n", [(11, 13, 7), (58, 3, 2), (2, 139, 2)])
+def test_odd_and_prime_lengths(emu, orc, n):
+    assert run_3d(emu, orc, n, n, CCC, (0, 1, 2), (0, 1, 2)) < TOL[8]
+    assert run_3d(emu, orc, n, n, CCC_B, (0, 1, 2), (2, 1, 0)) < TOL[8]
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (0, 1, 2), cs2=0) < TOL[8]
+    assert run_3d(emu, orc, half(n), n, CCR, (0, 1, 2), (0, 1, 2), cs1=0) < TOL[8]
+
+
+@pytest.mark.parametrize("mo1", PERMS)
+@pytest.mark.parametrize("mo2", PERMS)
+def test_all_memory_order_pairs(emu, orc, mo1, mo2):
+    """the 36 (mo1, mo2) pairs of sample/C/test3D_r2c_memord.c on one rank"""
+    n = (8, 6, 10)
+    assert run_3d(emu, orc, n, half(n), RCC, mo1, mo2, cs2=0) < TOL[8]
+    assert run_3d(emu, orc, half(n), n, CCR, mo2, mo1, cs1=0) < TOL[8]
+
+
+@pytest.mark.parametrize("m", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_pow2_c2c_sizes(emu, orc, m):
+    """every size of the register-radix fast path, transform dimension leading"""
+    n = (m, 3, 2)
+    err, out, want, desc = run_3d(emu, orc, n, n, ["CFFT_FORWARD_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"],
+                                  (0, 1, 2), (0, 1, 2), return_all=True)
+    assert any("pow2" in s["variant"] for s in desc["stages"]), desc
+    assert err < TOL[8]
+
+
+@pytest.mark.parametrize("m", [128, 512, 2048])
+def test_pow2_real_sizes(emu, orc, m):
+    n = (m, 2, 3)
+    err, _, _, desc = run_3d(emu, orc, n, half(n), ["R2CFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"], (0, 1, 2),
+                             (0, 1, 2), cs2=0, return_all=True)
+    assert "pow2" in desc["stages"][0]["variant"]
+    assert err < TOL[8]
+    err, _, _, desc = run_3d(emu, orc, half(n), n, ["C2RFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"], (0, 1, 2),
+                             (0, 1, 2), cs1=0, return_all=True)
+    assert "pow2" in desc["stages"][-1]["variant"]
+    assert err < TOL[8]
+
+
+@pytest.mark.parametrize("mo1,mo2", [((0, 1, 2), (1, 2, 0)), ((1, 2, 0), (0, 1, 2)), ((2, 1, 0), (1, 0, 2)), ((0, 2, 1), (2, 0, 1))])
+def test_pow2_strided_and_transposing(emu, orc, mo1, mo2):
+    """fast path with the transform dimension not leading on one or both sides (64 and 128 points)"""
+    n = (64, 128, 12)
+    assert run_3d(emu, orc, n, n, CCC, mo1, mo2) < TOL[8]
+    assert run_3d(emu, orc, n, half(n), RCC, mo1, mo2, cs2=0) < TOL[8]
+    assert run_3d(emu, orc, half(n), n, CCR, mo2, mo1, cs1=0) < TOL[8]
+
+
+def test_single_precision(emu, orc):
+    n = (64, 20, 6)
+    assert run_3d(emu, orc, n, n, CCC_S, (0, 1, 2), (0, 1, 2)) < TOL[4]
+    assert run_3d(emu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[4]
+    assert run_3d(emu, orc, half(n), n, CCR_S, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[4]
+
+
+@pytest.mark.parametrize("kind", R2R_KINDS)
+@pytest.mark.parametrize("variant", ["REAL_D", "COMPLEX_D", "REAL_S"])
+def test_r2r_kinds_1d(emu, orc, kind, variant, monkeypatch):
+    """all eight FFTW r2r kinds through the 1D API, transform along each dimension (test1D_cos.C / test1D_sin.C)"""
+    name = f"{kind}_{variant}"
+    if kind == "DCT4":
+        pytest.skip("DCT4 IDs follow the reference's registration (DCT-I planner); see test_dct4_quirk")
+    tol = TOL[4] if variant.endswith("_S") else TOL[8]
+    for dim, n in ((0, (9, 4, 3)), (1, (3, 12, 2)), (2, (2, 3, 7))):
+        assert run_1d(emu, orc, n, name, dim, (0, 1, 2), (0, 1, 2)) < tol
+    assert run_1d(emu, orc, (5, 6, 129 if kind == "DCT1" else 16), name, 2, (0, 1, 2), (2, 0, 1)) < tol
+
+
+@pytest.mark.parametrize("mo1", PERMS)
+@pytest.mark.parametrize("mo2", PERMS)
+def test_1d_r2c_all_orders(emu, orc, mo1, mo2):
+    """sample/C++/test_transplan.C matrix: 36 order pairs, each transform dimension"""
+    for dim in range(3):
+        assert run_1d(emu, orc, (8, 6, 4), "R2CFFT_D", dim, mo1, mo2) < TOL[8]
+
+
+@pytest.mark.parametrize("idir", [0, 1, 2])
+def test_fused_derivative(emu, orc, idir):
+    n = (16, 12, 10)
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, deriv=idir) < TOL[8]
+    n = (64, 9, 5)
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, deriv=idir) < TOL[8]
+    assert run_3d(emu, orc, n, n, CCC, (0, 1, 2), (0, 1, 2), deriv=idir) < TOL[8]
+
+
+def test_in_place(emu, orc):
+    """exec(AR, AR, true) as in sample/C++/test3D_c2c_inplace.C:204-236, plus R2C in place"""
+    n = (16, 12, 10)
+    assert run_3d(emu, orc, n, n, CCC, (0, 1, 2), (1, 2, 0), inplace=True) < TOL[8]
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (0, 1, 2), cs2=0, inplace=True) < TOL[8]
+    assert run_3d(emu, orc, n, n, ["EMPTY_TYPE_DOUBLE_COMPLEX"] * 3, (0, 1, 2), (2, 0, 1), inplace=True) < TOL[8]
+
+
+def test_empty_types_are_pure_permutations(emu, orc):
+    """empty transform = bit-exact reorder (reorder_out / reorder_in, exec.C:1858-2266)"""
+    n = (7, 5, 6)
+    for mo1 in PERMS:
+        for mo2 in PERMS:
+            err, out, want, _ = run_3d(emu, orc, n, n, ["EMPTY_TYPE_DOUBLE"] * 3, mo1, mo2, return_all=True)
+            assert np.array_equal(out, want)
+
+
+def test_2d_plus_empty(emu, orc):
+    """sample/C/test2D+empty.c: FFT in two dimensions, empty type in the middle one"""
+    n = (16, 6, 8)
+    t = ["R2CFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "CFFT_FORWARD_D"]
+    assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+
+
+def test_dct_in_3d(emu, orc):
+    """config C4 shape: R2C(x), C2C(y), DCT-I(z) on complex data, non-default output order"""
+    n = (16, 8, 9)
+    t = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
+    assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+    assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=1) < TOL[8]
+
+
+@pytest.mark.parametrize("mo", PERMS)
+@pytest.mark.parametrize("idir", [0, 1, 2])
+def test_compute_deriv_standalone(emu, orc, mo, idir):
+    """p3dfft_compute_deriv_double against deriv.C:85-185 (including its choice of storage dimension)"""
+    n = (9, 6, 5)
+    pg = emu.init_proc_grid([1, 1, 1])
+    g = emu.init_data_grid(n, 0, pg, [0, 1, 2], list(mo))
+    og = orc.OGrid(n, [0, 1, 2], mo, [1, 1, 1], 0, 0)
+    a = orc.local_of(orc.random_field(n, complex_=True), og)
+    out = np.zeros_like(a)
+    emu.compute_deriv(a, out, g, idir)
+    want = orc.compute_deriv_local(a, og, idir, mode="reference")
+    assert orc.rel_l2(out, want) < 1e-15
+    emu.free_data_grid(g)
+
+
+def test_dct4_quirk(pkg, orc):
+    """reference build/init.C:640-676 registers the DCT4 IDs with the DCT-I planner; the default build reproduces
+    that, P3DFFT_B200_TRUE_DCT4=1 gives FFTW_REDFT11.  Checked in subprocesses because setup() reads the env once."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import __graft_entry__ as ge
+from util import run_1d
+mod = ge.load_package(); orc = ge.load_oracle()
+lib = mod.load(emulated=True).setup()
+n = (9, 4, 3)
+pg = lib.init_proc_grid([1, 1, 1])
+g = lib.init_data_grid(n, -1, pg, [0, 1, 2], [0, 1, 2])
+plan = lib.plan_1Dtrans(g, g, "DCT4_REAL_D", 0)
+G = orc.random_field(n)
+og = orc.OGrid(n, [0, 1, 2], [0, 1, 2], [1, 1, 1], 0)
+a = orc.local_of(G, og); out = np.zeros_like(a)
+lib.exec_1Dtrans(plan, a, out, 0)
+e1 = orc.rel_l2(out, orc.local_of(orc.transform_1d(G, "dct1", 0), og))
+e4 = orc.rel_l2(out, orc.local_of(orc.transform_1d(G, "dct4", 0), og))
+print("RESULT", e1 < 1e-12, e4 < 1e-12)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    for env_val, want in (("0", "RESULT True False"), ("1", "RESULT False True")):
+        env = dict(os.environ, P3DFFT_B200_TRUE_DCT4=env_val)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert want in out.stdout, (out.stdout, out.stderr)

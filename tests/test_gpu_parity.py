@@ -1,0 +1,165 @@
+"""GPU parity tests (-m gpu): the product library on a real device against the oracle, all through the C ABI.
+
+Tolerances are the ones BASELINE.json:north_star states: relative L2 error <= 1e-12 (double), <= 1e-5 (single);
+pure permutations must be bit-exact."""
+import numpy as np
+import pytest
+
+from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
+from util import TOL, run_1d, run_3d
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(gpu):
+    assert "sm_100a" in gpu.version()
+    assert gpu.have_device()
+
+
+@pytest.mark.parametrize("n", [(16, 12, 10), (8, 9, 7), (30, 3, 14), (58, 139, 199)])
+def test_r2c_c2r_any_length(gpu, orc, n):
+    """includes the reference matrix's uneven grid 58x139x199 (extra/makejob.py:132)"""
+    assert run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+    assert run_3d(gpu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
+
+
+@pytest.mark.parametrize("mo1", PERMS)
+@pytest.mark.parametrize("mo2", PERMS)
+def test_all_memory_order_pairs(gpu, orc, mo1, mo2):
+    n = (128, 64, 96)
+    assert run_3d(gpu, orc, n, half(n), RCC, mo1, mo2, cs2=0) < TOL[8]
+    assert run_3d(gpu, orc, half(n), n, CCR, mo2, mo1, cs1=0) < TOL[8]
+
+
+@pytest.mark.parametrize("m", [64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("types", [CCC, CCC_B, CCC_S])
+def test_pow2_c2c_sizes(gpu, orc, m, types):
+    n = (m, 24, 20)
+    prec = 4 if types is CCC_S else 8
+    for mo1, mo2 in (((0, 1, 2), (0, 1, 2)), ((1, 0, 2), (1, 0, 2)), ((0, 1, 2), (1, 2, 0)), ((2, 1, 0), (0, 2, 1))):
+        assert run_3d(gpu, orc, n, n, types, mo1, mo2) < TOL[prec]
+
+
+@pytest.mark.parametrize("m", [128, 256, 512, 1024, 2048, 4096])
+def test_pow2_real_sizes(gpu, orc, m):
+    n = (m, 12, 10)
+    for mo1, mo2 in (((0, 1, 2), (0, 1, 2)), ((0, 1, 2), (1, 2, 0)), ((1, 2, 0), (0, 1, 2)), ((2, 0, 1), (1, 0, 2))):
+        assert run_3d(gpu, orc, n, half(n), RCC, mo1, mo2, cs2=0) < TOL[8]
+        assert run_3d(gpu, orc, half(n), n, CCR, mo2, mo1, cs1=0) < TOL[8]
+        assert run_3d(gpu, orc, n, half(n), RCC_S, mo1, mo2, cs2=0) < TOL[4]
+        assert run_3d(gpu, orc, half(n), n, CCR_S, mo2, mo1, cs1=0) < TOL[4]
+
+
+def test_config_c1_single_rank_128(gpu, orc):
+    """BASELINE config 1 grid (128^3 double R2C, X-pencil -> Z-pencil orders) on one rank + sine-wave known answer
+    of sample/C++/test3D_r2c.C:281-331"""
+    n = (128, 128, 128)
+    err, out, want, _ = run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, G=orc.sine_field(n), return_all=True)
+    spec = orc.from_storage(out, (1, 2, 0)) / np.prod(n)
+    expect = np.zeros_like(spec)
+    for sy, iy in ((1, 1), (-1, n[1] - 1)):
+        for sz, iz in ((1, 1), (-1, n[2] - 1)):
+            expect[1, iy, iz] = 0.125j * sy * sz
+    assert np.abs(spec - expect).max() < 1e-14 * n[0] * 0.25  # the reference's own gate
+    assert err < TOL[8]
+
+
+def test_config_c2_512_single(gpu, orc):
+    """BASELINE config 2: 512^3 C2C single precision, default memory ordering, checked against the oracle"""
+    n = (512, 512, 512)
+    assert run_3d(gpu, orc, n, n, CCC_S, (0, 1, 2), (0, 1, 2)) < TOL[4]
+
+
+def test_config_c4_dct_deriv(gpu, orc):
+    """BASELINE config 4 (reduced to 128x128x129): R2C(x), C2C(y), DCT-I(z), non-default order, derivative"""
+    n = (128, 128, 129)
+    t = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
+    assert run_3d(gpu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+    for idir in (0, 1):
+        assert run_3d(gpu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=idir) < TOL[8]
+    n = (64, 64, 128)  # awkward length: 2*(128-1) = 254 = 2*127
+    assert run_3d(gpu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+
+
+@pytest.mark.parametrize("kind", [k for k in R2R_KINDS if k != "DCT4"])
+@pytest.mark.parametrize("variant", ["REAL_D", "COMPLEX_D", "REAL_S", "COMPLEX_S"])
+def test_r2r_kinds(gpu, orc, kind, variant):
+    name = f"{kind}_{variant}"
+    tol = TOL[4] if variant.endswith("_S") else TOL[8]
+    for dim, n in ((0, (129, 14, 6)), (1, (12, 64, 5)), (2, (6, 9, 100))):
+        for mo1, mo2 in (((0, 1, 2), (0, 1, 2)), ((0, 1, 2), (2, 0, 1)), ((1, 2, 0), (0, 1, 2))):
+            assert run_1d(gpu, orc, n, name, dim, mo1, mo2) < tol
+
+
+@pytest.mark.parametrize("mo1", PERMS)
+@pytest.mark.parametrize("mo2", PERMS)
+def test_1d_r2c_all_orders(gpu, orc, mo1, mo2):
+    for dim in range(3):
+        assert run_1d(gpu, orc, (64, 48, 32), "R2CFFT_D", dim, mo1, mo2) < TOL[8]
+
+
+@pytest.mark.parametrize("idir", [0, 1, 2])
+def test_fused_derivative(gpu, orc, idir):
+    n = (128, 64, 32)
+    assert run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, deriv=idir) < TOL[8]
+    assert run_3d(gpu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0, deriv=idir) < TOL[4]
+    assert run_3d(gpu, orc, (30, 20, 18), (16, 20, 18), RCC, (0, 1, 2), (1, 2, 0), cs2=0, deriv=idir) < TOL[8]
+
+
+def test_in_place_and_empty(gpu, orc):
+    n = (64, 32, 48)
+    assert run_3d(gpu, orc, n, n, CCC, (0, 1, 2), (1, 2, 0), inplace=True) < TOL[8]
+    assert run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (0, 1, 2), cs2=0, inplace=True) < TOL[8]
+    for mo1 in PERMS:
+        for mo2 in PERMS:
+            err, out, want, _ = run_3d(gpu, orc, (17, 9, 12), (17, 9, 12), ["EMPTY_TYPE_DOUBLE"] * 3, mo1, mo2, return_all=True)
+            assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("mo", PERMS)
+@pytest.mark.parametrize("idir", [0, 1, 2])
+def test_compute_deriv_standalone(gpu, orc, mo, idir):
+    n = (65, 24, 20)
+    pg = gpu.init_proc_grid([1, 1, 1])
+    g = gpu.init_data_grid(n, 0, pg, [0, 1, 2], list(mo))
+    og = orc.OGrid(n, [0, 1, 2], mo, [1, 1, 1], 0, 0)
+    a = orc.local_of(orc.random_field(n, complex_=True), og)
+    out = np.zeros_like(a)
+    gpu.compute_deriv(a, out, g, idir)
+    assert orc.rel_l2(out, orc.compute_deriv_local(a, og, idir, mode="reference")) < 1e-15
+    gpu.free_data_grid(g)
+
+
+def test_device_pointers_roundtrip_1024_properties(gpu, orc):
+    """full-size config (1024^3 double R2C+C2R, device resident): size-independent properties -
+    round trip returns N*input and Parseval - since the oracle cannot hold this size in seconds"""
+    torch = pytest.importorskip("torch")
+    n = (1024, 1024, 1024)
+    pg = gpu.init_proc_grid([1, 1, 1])
+    g1 = gpu.init_data_grid(n, -1, pg, [0, 1, 2], [0, 1, 2])
+    g2 = gpu.init_data_grid(half(n), 0, pg, [0, 1, 2], [1, 2, 0])
+    pf = gpu.plan_3Dtrans(g1, g2, gpu.init_3Dtype(RCC))
+    pb = gpu.plan_3Dtrans(g2, g1, gpu.init_3Dtype(CCR))
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(n[2], n[1], n[0], device="cuda", dtype=torch.float64, generator=gen)
+    X = torch.empty(n[1] * n[2] * (n[0] // 2 + 1), device="cuda", dtype=torch.complex128)
+    y = torch.empty_like(x)
+    gpu.exec_3Dtrans(pf, x, X, 0)
+    gpu.exec_3Dtrans(pb, X, y, 1)
+    gpu.sync()
+    N = float(np.prod(n))
+    y.div_(N).sub_(x)
+    rt = (torch.linalg.vector_norm(y) / torch.linalg.vector_norm(x)).item()
+    assert rt < TOL[8], rt
+    # Parseval with Hermitian weights: sum |x|^2 = (1/N) (2 sum |X|^2 - sum_{kx=0} |X|^2 - sum_{kx=N/2} |X|^2)
+    gpu.exec_3Dtrans(pf, x, X, 0)
+    gpu.sync()
+    Xv = torch.view_as_real(X).view(n[1], n[0] // 2 + 1, n[2], 2)  # storage (y, x, z) for memory order {1,2,0}
+    p2 = (Xv ** 2).sum(dim=-1)
+    tot = 2 * p2.sum() - p2[:, 0, :].sum() - p2[:, n[0] // 2, :].sum()
+    lhs = (x ** 2).sum()
+    assert abs((tot / N - lhs) / lhs).item() < 1e-12
+    del x, X, y, Xv, p2
+    torch.cuda.empty_cache()
+    gpu.free_data_grid(g1)
+    gpu.free_data_grid(g2)

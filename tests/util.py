@@ -1,0 +1,93 @@
+"""helpers shared by the parity tests: run one transform through the C ABI and compare with the oracle"""
+import numpy as np
+
+TOL = {8: 1e-12, 4: 1e-5}  # relative L2 error bounds stated by BASELINE.json:north_star
+
+
+def np_dtype(dt, prec):
+    if dt == 2:
+        return np.complex128 if prec == 8 else np.complex64
+    return np.float64 if prec == 8 else np.float32
+
+
+def run_3d(lib, orc, gdims1, gdims2, types, mo1, mo2, dmap1=(0, 1, 2), dmap2=(0, 1, 2), cs1=-1, cs2=-1, procdims=(1, 1, 1),
+           rank=0, G=None, deriv=-1, inplace=False, key=20240, return_all=False):
+    """single-rank 3D transform of a random field; returns rel-L2 error against the oracle"""
+    k0, dt_in, _, prec = orc.type_info(types[orc.transform_order(types)[0]])
+    _, _, dt_out, _ = orc.type_info(types[orc.transform_order(types)[-1]])
+    for t in types:  # empty types keep the datatype
+        kk, a, b, _ = orc.type_info(t)
+    has_r2c = any(orc.type_info(t)[0] == "r2c" for t in types)
+    has_c2r = any(orc.type_info(t)[0] == "c2r" for t in types)
+    if has_r2c:
+        dt_in, dt_out = 1, 2
+    elif has_c2r:
+        dt_in, dt_out = 2, 1
+    single = prec == 4
+    pg = lib.init_proc_grid(list(procdims))
+    g1 = lib.init_data_grid(gdims1, cs1, pg, list(dmap1), list(mo1))
+    g2 = lib.init_data_grid(gdims2, cs2, pg, list(dmap2), list(mo2))
+    t3 = lib.init_3Dtype(list(types))
+    plan = lib.plan_3Dtrans(g1, g2, t3)
+    desc = lib.describe_plan3d(plan)
+    assert desc["ok"], desc
+    if G is None:
+        if has_c2r:  # Hermitian-consistent input: forward transform of a real field
+            fwd = [("R2CFFT_D" if orc.type_info(t)[0] == "c2r" else
+                    ("CFFT_FORWARD_D" if orc.type_info(t)[0] == "bwd" else "EMPTY_TYPE_DOUBLE_COMPLEX")) for t in types]
+            G = orc.transform_global(orc.random_field(gdims2, key=key), fwd)
+        else:
+            G = orc.random_field(gdims1, complex_=(dt_in == 2), key=key)
+    og1 = orc.OGrid(gdims1, dmap1, mo1, procdims, rank, cs1)
+    og2 = orc.OGrid(gdims2, dmap2, mo2, procdims, rank, cs2)
+    a = orc.local_of(G, og1).astype(np_dtype(dt_in, prec))
+    want = orc.local_of(orc.transform_global(G, types, gdims2, deriv_dim=deriv), og2)
+    if inplace:
+        n1 = a.size * (2 if dt_in == 2 else 1)
+        n2 = int(np.prod(og2.storage_shape())) * (2 if dt_out == 2 else 1)
+        buf = np.zeros(max(n1, n2), dtype=np.float32 if single else np.float64)
+        buf[:n1] = a.view(buf.dtype).ravel()
+        if deriv >= 0:
+            lib.exec_3Dderiv(plan, buf, buf, deriv, 1, single=single)
+        else:
+            lib.exec_3Dtrans(plan, buf, buf, 1, single=single)
+        out = buf[:n2].view(np_dtype(dt_out, prec)).reshape(og2.storage_shape())
+    else:
+        out = np.full(og2.storage_shape(), np.nan, dtype=np_dtype(dt_out, prec))
+        a0 = a.copy()
+        if deriv >= 0:
+            lib.exec_3Dderiv(plan, a, out, deriv, 0, single=single)
+        else:
+            lib.exec_3Dtrans(plan, a, out, 0, single=single)
+        assert np.array_equal(a, a0), "input was modified although OW == 0"
+    lib.free_data_grid(g1)
+    lib.free_data_grid(g2)
+    err = orc.rel_l2(out, want)
+    if return_all:
+        return err, out, want, desc
+    return err
+
+
+def run_1d(lib, orc, gdims, type_name, dim, mo1, mo2, key=7):
+    """transplan-style 1D transform (p3dfft_plan_1Dtrans) on one rank"""
+    kind, dt_in, dt_out, prec = orc.type_info(type_name)
+    single = prec == 4
+    gd2 = list(gdims)
+    if kind == "r2c":
+        gd2[dim] = gdims[dim] // 2 + 1
+    pg = lib.init_proc_grid([1, 1, 1])
+    g1 = lib.init_data_grid(gdims, -1, pg, [0, 1, 2], list(mo1))
+    g2 = lib.init_data_grid(gd2, dim if kind == "r2c" else -1, pg, [0, 1, 2], list(mo2))
+    plan = lib.plan_1Dtrans(g1, g2, type_name, dim)
+    desc = lib.describe_plan1d(plan)
+    assert desc["ok"], desc
+    G = orc.random_field(gdims, complex_=(dt_in == 2), key=key)
+    og1 = orc.OGrid(gdims, [0, 1, 2], mo1, [1, 1, 1], 0)
+    og2 = orc.OGrid(gd2, [0, 1, 2], mo2, [1, 1, 1], 0)
+    a = orc.local_of(G, og1).astype(np_dtype(dt_in, prec))
+    out = np.full(og2.storage_shape(), np.nan, dtype=np_dtype(dt_out, prec))
+    lib.exec_1Dtrans(plan, a, out, 0, single=single)
+    want = orc.local_of(orc.transform_1d(G, kind, dim), og2)
+    lib.free_data_grid(g1)
+    lib.free_data_grid(g2)
+    return orc.rel_l2(out, want)
