@@ -2,6 +2,7 @@
 // memory, twiddle tables, stage planning (kernel variant + tile shape) and launch, stand-alone
 // spectral derivative, CUDA-IPC peer mapping and the stream-ordered peer barrier.
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <atomic>
 #include <cmath>
@@ -465,8 +466,20 @@ int p3dfftcu_peer_barrier(void *const *peer_flags, const int *peer_slots, int n,
   CK(cudaGetLastError());
   return 0;
 #else
+  // CPU emulation: same protocol with host atomics on the shared-memory "device" buffers
   (void)stream;
-  return failmsg("peer barrier is not available in the CPU emulation build");
+  for (int j = 0; j < n; j++) __atomic_store_n(p.peer[j] + p.my_slot, p.epoch, __ATOMIC_RELEASE);
+  for (int j = 0; j < n; j++) {
+    long spins = 0;
+    while (__atomic_load_n(p.mine + p.slot[j], __ATOMIC_ACQUIRE) < p.epoch) {
+      if (++spins > 2000) {
+        struct timespec ts = {0, 100000};
+        nanosleep(&ts, nullptr);
+      }
+      if (spins > 600000) return failmsg("peer barrier timed out (emulation)");
+    }
+  }
+  return 0;
 #endif
 }
 

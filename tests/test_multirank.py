@@ -1,0 +1,114 @@
+"""N>1 path on CPU: planner + executor + fused exchange (peer stores, flag barrier) across real processes.
+
+Each rank is a process of the mini-MPI world (include/compat/mpi.h) running the CPU-thread emulation build, in
+which "device" buffers are POSIX shared memory and the CUDA-IPC mapping / peer barrier run unchanged.  Every rank
+compares its local output with the oracle's slice of the global transform (tests/mp_worker.py).  One test uses
+torch.distributed.run + gloo, the launcher and environment bench.py runs under on the GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from cases import CCC, CCR, RCC, RCC_S, half
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+XP = dict(dmap1=[0, 1, 2], mo1=[0, 1, 2], dmap2=[1, 2, 0], mo2=[1, 2, 0])  # X-pencil -> Z-pencil (test3D_r2c.C:153-179)
+
+
+def fwd(n, pd, types=RCC, **kw):
+    c = dict(types=types, procdims=pd, gdims1=list(n), gdims2=list(half(n)), cs2=0, **XP)
+    c.update(kw)
+    return c
+
+
+def bwd(n, pd, types=CCR, **kw):
+    c = dict(types=types, procdims=pd, gdims1=list(half(n)), gdims2=list(n), cs1=0, dmap1=XP["dmap2"], mo1=XP["mo2"],
+             dmap2=XP["dmap1"], mo2=XP["mo1"])
+    c.update(kw)
+    return c
+
+
+def c2c(n, pd, **kw):
+    c = dict(types=CCC, procdims=pd, gdims1=list(n), gdims2=list(n), **XP)
+    c.update(kw)
+    return c
+
+
+def launch(nranks, cases, mode="emu", gloo=False, timeout=900):
+    arg = json.dumps(cases)
+    if gloo:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 2000), os.path.join(HERE, "mp_worker.py"), mode, arg, "--gloo"]
+    else:
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "mpirun.py"), "-np", str(nranks), sys.executable,
+               os.path.join(HERE, "mp_worker.py"), mode, arg]
+    env = dict(os.environ)
+    env.pop("P3DFFT_B200_PLAN_ONLY", None)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    ok = out.returncode == 0 and out.stdout.count(" OK worst") == nranks
+    assert ok, (out.stdout[-3000:], out.stderr[-3000:])
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _emu_built(emu):
+    return emu
+
+
+def test_pencil_2x2_config_c1_shape():
+    """BASELINE config 1 shape (2x2 pencil grid on 4 ranks), reduced to 32x24x20 + the uneven split 9 = 4|5"""
+    n = (32, 24, 20)
+    launch(4, [fwd(n, [1, 2, 2]), bwd(n, [1, 2, 2]), fwd((16, 12, 10), [1, 2, 2]), bwd((16, 12, 10), [1, 2, 2])])
+
+
+def test_slab_and_row_grids():
+    """slab {1,1,P} (one exchange) and {1,P,1}; uneven blocks (10 = 3|3|4 over 3 ranks does not occur with P=2,4: use 4)"""
+    n = (16, 14, 10)
+    launch(4, [fwd(n, [1, 1, 4]), bwd(n, [1, 1, 4]), fwd(n, [1, 4, 1]), bwd(n, [1, 4, 1]), c2c(n, [1, 1, 4])])
+
+
+def test_world_size_2_gloo_torchrun():
+    """world_size 2 under torch.distributed.run with a gloo group next to the library's own rendezvous"""
+    n = (16, 12, 10)
+    launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2]), fwd(n, [1, 2, 1])], gloo=True)
+
+
+def test_uneven_and_prime_sizes_3_ranks():
+    n = (14, 7, 11)
+    launch(3, [fwd(n, [1, 1, 3]), bwd(n, [1, 1, 3]), c2c((5, 7, 11), [1, 3, 1])])
+
+
+def test_pow2_kernels_with_exchange_segments():
+    """64-point stages take the register-radix kernel; its stores go through the per-peer segment table"""
+    n = (128, 64, 64)
+    launch(2, [fwd(n, [1, 1, 2], reps=1), bwd(n, [1, 1, 2], reps=1)], timeout=1500)
+    launch(4, [fwd((128, 64, 4), [1, 2, 2], reps=1), bwd((128, 64, 4), [1, 2, 2], reps=1)], timeout=1500)
+
+
+def test_memory_orders_and_derivative_multirank():
+    n = (16, 12, 10)
+    cs = []
+    for mo1, mo2 in (([1, 0, 2], [2, 1, 0]), ([2, 0, 1], [0, 2, 1]), ([0, 2, 1], [1, 0, 2])):
+        cs.append(fwd(n, [1, 2, 2], mo1=mo1, mo2=mo2))
+        cs.append(bwd(n, [1, 2, 2], mo1=mo2, mo2=mo1))
+    for idir in (0, 1, 2):
+        cs.append(fwd(n, [1, 2, 2], deriv=idir))
+    cs.append(fwd(n, [1, 2, 2], types=RCC_S))
+    launch(4, cs)
+
+
+def test_other_distributions_and_empty_types():
+    """same distribution in and out, Y-pencil outputs, and MPI-only redistribution of an untransformed array"""
+    n = (12, 10, 8)
+    e = ["EMPTY_TYPE_DOUBLE"] * 3
+    cs = [
+        c2c(n, [1, 2, 2], dmap2=[0, 1, 2], mo2=[0, 1, 2]),                 # in and out both X-pencils
+        c2c(n, [1, 2, 2], dmap2=[1, 0, 2], mo2=[1, 0, 2]),                 # Y-pencil output
+        c2c(n, [1, 2, 2], dmap1=[2, 1, 0], mo1=[2, 1, 0], dmap2=[0, 1, 2], mo2=[0, 1, 2]),
+        dict(types=e, procdims=[1, 2, 2], gdims1=list(n), gdims2=list(n), dmap1=[0, 1, 2], mo1=[0, 1, 2], dmap2=[1, 2, 0], mo2=[2, 0, 1]),
+        dict(types=["R2CFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "CFFT_FORWARD_D"], procdims=[1, 2, 2], gdims1=list(n), gdims2=list(half(n)),
+             cs2=0, **XP),                                                 # sample/C/test2D+empty.c
+    ]
+    launch(4, cs)

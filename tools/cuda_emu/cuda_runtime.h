@@ -85,8 +85,10 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
   strcpy(p->name, "EMULATED (CPU threads)"); p->major = 10; p->minor = 0; p->multiProcessorCount = 2;
   p->sharedMemPerBlockOptin = 232448; return cudaSuccess;
 }
-inline cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~size_t(255)); return *p ? 0 : 2; }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+// "device" allocations live in POSIX shared memory so that the CUDA-IPC calls below can map a peer
+// process's buffer: multi-rank exchanges (peer stores + flag barrier) run on the CPU exactly as written
+cudaError_t cudaMalloc(void **p, size_t n);
+cudaError_t cudaFree(void *p);
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
@@ -97,6 +99,6 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return 1; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, int) { return 1; }
-inline cudaError_t cudaIpcCloseMemHandle(void *) { return 1; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *);
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, int);
+cudaError_t cudaIpcCloseMemHandle(void *);
