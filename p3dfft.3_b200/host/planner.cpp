@@ -111,12 +111,22 @@ struct ProtoStage {
   int gd_in[3], gd_out[3];
   int dmap_in[3], dmap_out[3];
   int ld_in[3], ld_out[3];
+  int rep_in[3], rep_out[3];  // largest block of each dimension over all ranks: rank-independent input of the layout choice
 };
 
 void local_dims(const ProcGrid *pg, const int gd[3], const int dmap[3], int ld[3]) {
   for (int i = 0; i < 3; i++) {
     int st;
     block(gd[i], pg->ProcDims[dmap[i]], pg->grid_id_cart[dmap[i]], &st, &ld[i]);
+  }
+}
+
+// every rank must pick the same intermediate storage orders (senders address their peers' arrays), so the
+// layout search sees the largest block of each dimension instead of this rank's own block
+void rep_dims(const ProcGrid *pg, const int gd[3], const int dmap[3], int rd[3]) {
+  for (int i = 0; i < 3; i++) {
+    int p = pg->ProcDims[dmap[i]];
+    rd[i] = gd[i] / p + (gd[i] % p ? 1 : 0);
   }
 }
 
@@ -181,6 +191,8 @@ bool build_protos(const std::vector<Op> &ops, const DataGrid &g1, const DataGrid
     memcpy(s.dmap_out, dmap, sizeof dmap);
     local_dims(pg, s.gd_in, s.dmap_in, s.ld_in);
     local_dims(pg, s.gd_out, s.dmap_out, s.ld_out);
+    rep_dims(pg, s.gd_in, s.dmap_in, s.rep_in);
+    rep_dims(pg, s.gd_out, s.dmap_out, s.rep_out);
     out->push_back(s);
   }
   for (int i = 0; i < 3; i++)
@@ -194,7 +206,11 @@ bool build_protos(const std::vector<Op> &ops, const DataGrid &g1, const DataGrid
     ProtoStage s;
     memset(&s, 0, sizeof s);
     s.kind = P3DFFTCU_K_EMPTY;
-    s.dim = lead_dim(g2.MemOrder, g2.Ldims);
+    {
+      int rd[3];
+      rep_dims(pg, gd, dmap, rd);
+      s.dim = lead_dim(g2.MemOrder, rd);
+    }
     s.dt_in = s.dt_out = dt;
     s.nfft = s.n_in = s.n_out = gd[s.dim];
     s.xb = s.comm_dim = -1;
@@ -204,6 +220,8 @@ bool build_protos(const std::vector<Op> &ops, const DataGrid &g1, const DataGrid
     memcpy(s.dmap_out, dmap, sizeof dmap);
     local_dims(pg, gd, dmap, s.ld_in);
     local_dims(pg, gd, dmap, s.ld_out);
+    rep_dims(pg, gd, dmap, s.rep_in);
+    rep_dims(pg, gd, dmap, s.rep_out);
     out->push_back(s);
   }
   return true;
@@ -227,7 +245,7 @@ double choose_layouts(const std::vector<ProtoStage> &ps, const int mo1[3], const
         cur[s + 1] = (int)(x % 6);
         x /= 6;
       }
-      tot += stage_cost(ps[s].dim, prev, ps[s].ld_in, next, ps[s].ld_out);
+      tot += stage_cost(ps[s].dim, prev, ps[s].rep_in, next, ps[s].rep_out);
       prev = next;
     }
     if (tot < bestc - 1e-9) {

@@ -112,3 +112,28 @@ def test_other_distributions_and_empty_types():
              cs2=0, **XP),                                                 # sample/C/test2D+empty.c
     ]
     launch(4, cs)
+
+
+# ------------------------------------------------------------------------------------------------ real GPUs
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_gpu_multirank_parity(nranks):
+    """the same cases on N real GPUs (one process per GPU, peer stores over NVLink); skipped when the box has fewer"""
+    if _ngpu() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    n = (128, 96, 64)
+    grids = [[1, 1, nranks]] + ([[1, 2, nranks // 2]] if nranks >= 4 else [[1, nranks, 1]])
+    cs = []
+    for pd in grids:
+        cs += [fwd(n, pd), bwd(n, pd), fwd(n, pd, types=RCC_S), fwd(n, pd, deriv=1), c2c((64, 50, 36), pd)]
+    cs.append(fwd((58, 139, 199), grids[0]))
+    cs.append(bwd((58, 139, 199), grids[-1]))
+    launch(nranks, cs, mode="gpu", timeout=1200)
