@@ -49,10 +49,18 @@ for _num in (1, 2, 3, 4):
 TYPE_ID = {t[0]: i for i, t in enumerate(TYPE_TABLE)}
 
 
+# The reference registers its four DCT4 IDs with the DCT-I planner (build/init.C:640,652,664,676: plan_dct1_*), so
+# a "DCT4" request executes FFTW_REDFT00.  Pinned by the golden cases t1d_DCT4_REAL_D_* (reference host code).
+REFERENCE_DCT4_IS_DCT1 = True
+
+
 def type_info(t):
-    """(kind, dt_in, dt_out, prec) of a type given by name or ID"""
+    """(kind, dt_in, dt_out, prec) of a type given by name or ID, with the reference's DCT4 registration quirk"""
     rec = TYPE_TABLE[TYPE_ID[t]] if isinstance(t, str) else TYPE_TABLE[int(t)]
-    return rec[1], rec[2], rec[3], rec[4]
+    kind = rec[1]
+    if kind == "dct4" and REFERENCE_DCT4_IS_DCT1:
+        kind = "dct1"
+    return kind, rec[2], rec[3], rec[4]
 
 
 # ---------------------------------------------------------------------------------------------- geometry

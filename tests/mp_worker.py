@@ -14,11 +14,12 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 import __graft_entry__ as ge  # noqa: E402
-from util import TOL, np_dtype  # noqa: E402
+from util import TOL, check_golden, np_dtype  # noqa: E402
 
 
 def main():
-    mode, cases = sys.argv[1], json.loads(sys.argv[2])
+    mode = sys.argv[1]
+    cases = [] if sys.argv[2] == "golden" else json.loads(sys.argv[2])
     rank = int(os.environ.get("P3DFFT_RANK", os.environ.get("RANK", "0")))
     world = int(os.environ.get("P3DFFT_NRANKS", os.environ.get("WORLD_SIZE", "1")))
     use_gloo = "--gloo" in sys.argv
@@ -30,6 +31,9 @@ def main():
     orc = ge.load_oracle()
     lib = mod.load(emulated=(mode == "emu")).setup()
     worst = 0.0
+    if sys.argv[2] == "golden":  # every golden case recorded on this many ranks, against the reference's own arrays
+        n = check_golden(lib, orc, None, rank=rank, world=world)
+        assert n > 0, "no golden case for this world size"
     for c in cases:
         types, pd = c["types"], c["procdims"]
         assert pd[0] * pd[1] * pd[2] == world, (pd, world)

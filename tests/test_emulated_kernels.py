@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
-from util import TOL, run_1d, run_3d
+from util import TOL, check_golden, run_1d, run_3d
 
 
 @pytest.mark.parametrize("n", [(16, 12, 10), (8, 9, 7), (6, 5, 4), (30, 3, 14)])
@@ -179,3 +179,9 @@ print("RESULT", e1 < 1e-12, e4 < 1e-12)
         env = dict(os.environ, P3DFFT_B200_TRUE_DCT4=env_val)
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert want in out.stdout, (out.stdout, out.stderr)
+
+
+def test_reference_golden_vectors_single_rank(emu, orc):
+    """every single-rank golden case (tests/golden: arrays written by the reference's own host code): all 36 memory-order
+    pairs, C2R, the 1D API with the r2r kinds, stand-alone compute_deriv, the DCT4 registration quirk"""
+    assert check_golden(emu, orc, None, rank=0, world=1) >= 100

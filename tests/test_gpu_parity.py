@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
-from util import TOL, run_1d, run_3d
+from util import TOL, check_golden, run_1d, run_3d
 
 pytestmark = pytest.mark.gpu
 
@@ -163,3 +163,9 @@ def test_device_pointers_roundtrip_1024_properties(gpu, orc):
     torch.cuda.empty_cache()
     gpu.free_data_grid(g1)
     gpu.free_data_grid(g2)
+
+
+def test_reference_golden_vectors_single_rank(gpu, orc):
+    """every single-rank golden case (tests/golden: arrays written by the reference's own host code): all 36 memory-order
+    pairs, C2R, the 1D API with the r2r kinds, stand-alone compute_deriv, the DCT4 registration quirk"""
+    assert check_golden(gpu, orc, None, rank=0, world=1) >= 100

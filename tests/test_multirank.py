@@ -38,7 +38,7 @@ def c2c(n, pd, **kw):
 
 
 def launch(nranks, cases, mode="emu", gloo=False, timeout=900):
-    arg = json.dumps(cases)
+    arg = cases if isinstance(cases, str) else json.dumps(cases)
     if gloo:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), os.path.join(HERE, "mp_worker.py"), mode, arg, "--gloo"]
@@ -61,6 +61,12 @@ def test_pencil_2x2_config_c1_shape():
     """BASELINE config 1 shape (2x2 pencil grid on 4 ranks), reduced to 32x24x20 + the uneven split 9 = 4|5"""
     n = (32, 24, 20)
     launch(4, [fwd(n, [1, 2, 2]), bwd(n, [1, 2, 2]), fwd((16, 12, 10), [1, 2, 2]), bwd((16, 12, 10), [1, 2, 2])])
+
+
+@pytest.mark.parametrize("nranks", [3, 4])
+def test_reference_golden_vectors_multirank(nranks):
+    """per-rank outputs of the reference's own host code (tests/golden) on 3 and 4 ranks"""
+    launch(nranks, "golden")
 
 
 def test_slab_and_row_grids():
@@ -137,3 +143,5 @@ def test_gpu_multirank_parity(nranks):
     cs.append(fwd((58, 139, 199), grids[0]))
     cs.append(bwd((58, 139, 199), grids[-1]))
     launch(nranks, cs, mode="gpu", timeout=1200)
+    if nranks == 4:
+        launch(4, "golden", mode="gpu")

@@ -91,3 +91,76 @@ def run_1d(lib, orc, gdims, type_name, dim, mo1, mo2, key=7):
     lib.free_data_grid(g1)
     lib.free_data_grid(g2)
     return orc.rel_l2(out, want)
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+def golden():
+    """(index, npz, make_golden module) of tests/golden/reference_golden.npz (produced by the reference's host code)"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    with open(os.path.join(here, "index.json")) as f:
+        index = json.load(f)
+    return index, np.load(os.path.join(here, "reference_golden.npz")), mg
+
+
+def golden_case(z, name):
+    import json
+    return json.loads(str(z[name + "/case"]))
+
+
+def exec_case(lib, orc, mg, c, rank):
+    """run one golden-format case on this rank through the C ABI; returns (output array, grid1, grid2 geometry lists)"""
+    dt_in, dt_out, prec = mg.case_types(c)
+    single = prec == 4
+    pd = c["procdims"]
+    pg = lib.init_proc_grid(pd)
+    g1 = lib.init_data_grid(c["gdims1"], c["cs1"], pg, c["dmap1"], c["mo1"])
+    g2 = lib.init_data_grid(c["gdims2"], c["cs2"], pg, c["dmap2"], c["mo2"])
+    og1 = orc.OGrid(c["gdims1"], c["dmap1"], c["mo1"], pd, rank, c["cs1"])
+    og2 = orc.OGrid(c["gdims2"], c["dmap2"], c["mo2"], pd, rank, c["cs2"])
+    geo = list(g1.contents.Ldims) + list(g1.contents.GlobStart) + list(g2.contents.Ldims) + list(g2.contents.GlobStart)
+    a = orc.local_of(mg.global_input(c), og1).astype(np_dtype(dt_in, prec))
+    if c["mode"] == "deriv":
+        out = np.full(og1.storage_shape(), np.nan, dtype=np_dtype(dt_out, prec))
+        lib.compute_deriv(a, out, g1, c["idir"], single=single)
+    else:
+        out = np.full(og2.storage_shape(), np.nan, dtype=np_dtype(dt_out, prec))
+        if c["mode"] == "3d":
+            plan = lib.plan_3Dtrans(g1, g2, lib.init_3Dtype(c["types"]))
+            assert lib.describe_plan3d(plan)["ok"]
+            if c["idir"] >= 0:
+                lib.exec_3Dderiv(plan, a, out, c["idir"], 0, single=single)
+            else:
+                lib.exec_3Dtrans(plan, a, out, 0, single=single)
+        else:
+            plan = lib.plan_1Dtrans(g1, g2, c["types"][0], c["dim"])
+            assert lib.describe_plan1d(plan)["ok"]
+            lib.exec_1Dtrans(plan, a, out, 0, single=single)
+    lib.free_data_grid(g1)
+    lib.free_data_grid(g2)
+    return out, geo
+
+
+def check_golden(lib, orc, names, rank=0, world=1):
+    """run the named golden cases whose rank count equals `world`; compare with the reference's arrays"""
+    index, z, mg = golden()
+    done = 0
+    for name in names or index:
+        c = golden_case(z, name)
+        pd = c["procdims"]
+        if pd[0] * pd[1] * pd[2] != world:
+            continue
+        out, geo = exec_case(lib, orc, mg, c, rank)
+        ref = z[f"{name}/out_{rank}"]
+        assert geo == list(z[f"{name}/meta_{rank}"]), (name, geo)
+        prec = mg.case_types(c)[2]
+        if ref.size:
+            err = orc.rel_l2(out.ravel(), ref)
+            assert err < TOL[prec], (name, rank, err)
+        done += 1
+    return done
