@@ -17,6 +17,7 @@
 // R2C uses the length-N/2 complex FFT of the even/odd-packed real data plus a Hermitian split;
 // C2R is the mirror image.  Backward transforms use conj(F(conj(x))).
 #pragma once
+#include <cstdlib>
 #include <string>
 #include "common.cuh"
 
@@ -169,7 +170,7 @@ __device__ __forceinline__ void smem_gather(typename cx<T>::type *v, const typen
 
 // ------------------------------------------------------------------ the kernel
 template <typename T, int M, int THREADS>
-__global__ void __launch_bounds__(THREADS) pow2_stage_kernel(const __grid_constant__ StageParams P) {
+__device__ __forceinline__ void pow2_stage_body(const StageParams &P) {
   typedef typename cx<T>::type C;
   typedef Pow2Cfg<M> Cfg;
   constexpr int E = Cfg::E, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
@@ -314,6 +315,18 @@ __global__ void __launch_bounds__(THREADS) pow2_stage_kernel(const __grid_consta
   }
 }
 
+// MINB = resident CTAs per SM the register allocation must allow (caps registers at 65536 / (THREADS * MINB))
+template <typename T, int M, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) pow2_stage_kernel(const __grid_constant__ StageParams P) {
+  pow2_stage_body<T, M, THREADS>(P);
+}
+
+// register budget: 128 per thread in double (16 complex values = 64 registers + butterfly temporaries),
+// 80 in single -> 512 resp. 768 resident threads per SM whatever the CTA size
+template <typename T, int THREADS> struct Pow2MinBlocks {
+  enum { BUDGET = sizeof(T) == 8 ? 512 : 768, VALUE = (BUDGET / THREADS) < 1 ? 1 : (BUDGET / THREADS) };
+};
+
 // ------------------------------------------------------------------ host side
 struct Pow2Plan {
   int M = 0, prec = 0, threads = 0, grid = 0;
@@ -337,11 +350,11 @@ inline bool pow2_supported(const p3dfftcu_stage_desc &d) {
 
 template <typename T, int M, int THREADS> void pow2_launcher(const StageParams &P, int grid, int threads, size_t smem, cudaStream_t s) {
   (void)threads;
-  P3B_LAUNCH((pow2_stage_kernel<T, M, THREADS>), grid, THREADS, smem, s, P);
+  P3B_LAUNCH((pow2_stage_kernel<T, M, THREADS, Pow2MinBlocks<T, THREADS>::VALUE>), grid, THREADS, smem, s, P);
 }
 
 template <typename T, int M, int THREADS> int pow2_bind(Pow2Plan *pl, size_t smem_optin, int num_sms) {
-  auto kern = pow2_stage_kernel<T, M, THREADS>;
+  auto kern = pow2_stage_kernel<T, M, THREADS, Pow2MinBlocks<T, THREADS>::VALUE>;
   constexpr int TP = M / Pow2Cfg<M>::E;
   int npb = THREADS / TP;
   pl->threads = THREADS;
@@ -415,6 +428,10 @@ inline int pow2_setup(const p3dfftcu_stage_desc &d, int num_sms, size_t smem_opt
   size_t esz = (size_t)d.prec * 2;
   int want = (needU || needV) ? (int)(128 / esz) : 4;  // 128-byte runs across pencils when transposing
   if (needU && needV) want = 16;
+  if (const char *e = getenv("P3DFFT_B200_POW2_PENCILS")) {  // tuning override: pencils per CTA iteration
+    int w = atoi(e);
+    if (w > 0) want = w;
+  }
   pl->M = M;
   pl->prec = d.prec;
   int rc = d.prec == 8 ? pow2_bind_any<double>(pl, M, want, smem_optin, num_sms) : pow2_bind_any<float>(pl, M, want, smem_optin, num_sms);
