@@ -27,7 +27,14 @@ $(OBJDIR)/gpu_layer.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) in
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o
+# pipelined pow2 kernels: one object per (precision, kind)
+PIPEKEYS := 4_1 4_2 4_3 4_4 8_1 8_2 8_3 8_4
+PIPEOBJ  := $(PIPEKEYS:%=$(OBJDIR)/pipe_%.o)
+$(OBJDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+
+$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(PIPEOBJ)
 	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static -ldl -lrt -lpthread
 
 emu: $(EMULIB)
@@ -37,7 +44,11 @@ $(EMUDIR)/gpu_layer_emu.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh
 $(EMUDIR)/emu_globals.o: tools/cuda_emu/emu_globals.cpp tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
 	$(CXX) -O1 -std=c++17 -fPIC -Itools/cuda_emu -c $< -o $@
-$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o
+EMUPIPEOBJ := $(PIPEKEYS:%=$(EMUDIR)/pipe_%.o)
+$(EMUDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
+	@mkdir -p $(EMUDIR)
+	$(CXX) -O1 -std=c++17 -fPIC -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUPIPEOBJ)
 	$(CXX) -shared -o $@ $^ -lrt -lpthread
 
 clean:

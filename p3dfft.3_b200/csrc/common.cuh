@@ -51,7 +51,7 @@ struct StageParams {
   long long tiles_u, ntiles;
   int kind, dt_in, dt_out;
   int nfft, n_in, n_out, L;  // L = length of the internal complex FFT
-  int tile_u, tile_v;
+  int tile_u, tile_v, tu_log2;
   int load_ord, store_ord;
   int lstride;               // shared-memory pitch of one pencil (complex elements)
   int nfac;

@@ -18,8 +18,31 @@
 #include "common.cuh"
 #include "generic_stage.cuh"
 #include "pow2_stage.cuh"
+#include "pow2_pipe.cuh"
 
 using namespace p3b;
+
+namespace p3b {
+#define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int ld, int M, int P);
+P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4)
+P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4)
+#undef P3B_DECL_PIPE
+const PipeInfo *pipe_lookup(int prec, int kind, int ld, int M, int P) {
+  if (prec == 4) switch (kind) {
+      case 1: return pipe_lookup_p4_1(ld, M, P);
+      case 2: return pipe_lookup_p4_2(ld, M, P);
+      case 3: return pipe_lookup_p4_3(ld, M, P);
+      case 4: return pipe_lookup_p4_4(ld, M, P);
+    }
+  if (prec == 8) switch (kind) {
+      case 1: return pipe_lookup_p8_1(ld, M, P);
+      case 2: return pipe_lookup_p8_2(ld, M, P);
+      case 3: return pipe_lookup_p8_3(ld, M, P);
+      case 4: return pipe_lookup_p8_4(ld, M, P);
+    }
+  return nullptr;
+}
+}  // namespace p3b
 
 namespace {
 
@@ -139,7 +162,14 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
 #endif
 
 // ------------------------------------------------------------------ stage object
-enum Variant { V_GENERIC = 0, V_POW2 = 1 };
+enum Variant { V_GENERIC = 0, V_POW2 = 1, V_PIPE = 2 };
+
+struct PipePlan {
+  const p3b::PipeInfo *info = nullptr;
+  int M = 0, P = 0, ld = 0, grid = 0;
+  int tile_u = 1, tile_v = 1, tu_log2 = 0, load_ord = 0, store_ord = 0;
+  long long tiles_u = 0, ntiles = 0;
+};
 
 }  // namespace
 
@@ -151,6 +181,8 @@ struct p3dfftcu_stage_s {
   int grid;
   size_t smem;
   Pow2Plan pw;
+  PipePlan pp;
+  bool have_pw = false;  // the non-pipelined pow2 kernel is kept as the fallback for unaligned user pointers
   std::string name;
 };
 
@@ -240,6 +272,75 @@ template <typename T> int setup_generic(p3dfftcu_stage_s *st) {
   snprintf(nm, sizeof nm, "generic<%s> L=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d", sizeof(T) == 8 ? "f64" : "f32",
            P.L, tu, tv, P.load_ord, P.store_ord, st->smem, st->grid);
   st->name = nm;
+  return 0;
+}
+
+
+int ilog2(int x) {
+  int l = 0;
+  while ((1 << l) < x) l++;
+  return l;
+}
+
+// picks the pipelined kernel (pow2_pipe.cuh) for a stage; returns 0 ok, <0 not applicable, >0 CUDA error
+int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
+  if (!pow2_supported(d)) return -1;
+  const bool real = d.kind == P3DFFTCU_K_R2C || d.kind == P3DFFTCU_K_C2R;
+  const int M = real ? d.nfft / 2 : d.nfft;
+  int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
+  int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
+  const bool needU = fin == 1 || fout == 1, needV = fin == 2 || fout == 2;
+  int ld = LD_ELEM;
+  if (d.kind == P3DFFTCU_K_R2C && !(d.is_d == 1 && d.is_u % 2 == 0 && d.is_v % 2 == 0)) ld = LD_REAL;
+  const size_t esz = (size_t)d.prec * 2;
+  int want = (needU || needV) ? (int)(128 / esz) : 4;  // 128-byte runs across pencils when a side is transposed
+  if (ld == LD_REAL && fin != 0) want *= 2;           // runs of reals are half as long
+  if (needU && needV) want = 16;
+  if (const char *e = getenv("P3DFFT_B200_POW2_PENCILS")) {
+    int w = atoi(e);
+    if (w > 0) want = w;
+  }
+  long long npen = d.nu * d.nv;
+  while (want > 2 && want / 2 >= npen) want /= 2;
+  if (want > 16) want = 16;
+  const PipeInfo *info = nullptr;
+  int P = want;
+  for (; P >= 2; P /= 2) {
+    info = pipe_lookup(d.prec, d.kind, ld, M, P);
+    if (info && info->smem <= g_smem_optin) break;
+    info = nullptr;
+  }
+  if (!info) return -1;
+  int tu = P, tv = 1;
+  if (needU && needV) {
+    tu = 1;
+    while (tu * tu < P) tu *= 2;
+    tv = P / tu;
+  } else if (needV) {
+    tv = P;
+    tu = 1;
+  }
+  pp->info = info;
+  pp->M = M;
+  pp->P = P;
+  pp->ld = ld;
+  pp->tile_u = tu;
+  pp->tile_v = tv;
+  pp->tu_log2 = ilog2(tu);
+  pp->load_ord = fin == 0 ? ORD_D : (fin == 1 ? ORD_U : ORD_V);
+  pp->store_ord = fout == 0 ? ORD_D : (fout == 1 ? ORD_U : ORD_V);
+  pp->tiles_u = (d.nu + tu - 1) / tu;
+  pp->ntiles = pp->tiles_u * ((d.nv + tv - 1) / tv);
+  if (cudaFuncSetAttribute(info->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, info->func, info->threads, info->smem) != cudaSuccess) return 1;
+  if (occ < 1) occ = 1;
+  long long g = (long long)g_num_sms * occ;
+  pp->grid = (int)(pp->ntiles < g ? (pp->ntiles > 0 ? pp->ntiles : 1) : g);
+  char nm[220];
+  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,xs=%d,ld=%d> threads=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", M, P, info->xs, ld, info->threads, tu, tv, pp->load_ord, pp->store_ord, info->smem, pp->grid, occ);
+  *name = nm;
   return 0;
 }
 
@@ -348,8 +449,20 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) 
     bool allow_fast = !(force && atoi(force));
     if (allow_fast && pow2_supported(d)) {
       rc = pow2_setup(d, g_num_sms, g_smem_optin, &st->pw, &st->name);
-      if (!rc) st->variant = V_POW2;
-      else if (rc < 0) rc = 0;  // negative: not applicable, fall through to the generic kernel
+      if (!rc) {
+        st->variant = V_POW2;
+        st->have_pw = true;
+      } else if (rc < 0) rc = 0;  // negative: not applicable, fall through to the generic kernel
+      const char *nopipe = getenv("P3DFFT_B200_NO_PIPE");
+      if (!rc && st->have_pw && !(nopipe && atoi(nopipe))) {
+        std::string pname;
+        int prc = pipe_setup(d, &st->pp, &pname);
+        if (prc > 0) rc = failmsg("pipelined stage kernel setup failed");
+        else if (prc == 0) {
+          st->variant = V_PIPE;
+          st->name = pname;
+        }
+      }
     }
     if (!rc && st->variant == V_GENERIC) rc = d.prec == 8 ? setup_generic<double>(st) : setup_generic<float>(st);
   }
@@ -378,9 +491,23 @@ int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int
     if (slot < 0 || slot >= ndst || !dst[slot]) return failmsg("stage: missing destination buffer for a segment");
     P.seg[s].base = dst[slot];
   }
-  if (P.ntiles == 0 && st->variant == V_GENERIC) return 0;
+  if (P.ntiles == 0 && st->variant == V_GENERIC) return 0;  // (the generic plan's tile count; other variants carry their own)
   cudaStream_t cs = (cudaStream_t)stream;
-  if (st->variant == V_POW2) {
+  Variant variant = st->variant;
+  if (variant == V_PIPE) {
+    // cp.async needs element-aligned sources; an odd user pointer takes the non-pipelined kernel instead
+    const size_t need = (size_t)st->d.prec * (st->pp.ld == LD_REAL ? 1 : 2);
+    if (((uintptr_t)in) % need) variant = st->have_pw ? V_POW2 : V_GENERIC;
+  }
+  if (variant == V_PIPE) {
+    const PipePlan &pp = st->pp;
+    if (pp.ntiles > 0) {
+      P.tile_u = pp.tile_u; P.tile_v = pp.tile_v; P.tu_log2 = pp.tu_log2;
+      P.load_ord = pp.load_ord; P.store_ord = pp.store_ord;
+      P.tiles_u = pp.tiles_u; P.ntiles = pp.ntiles;
+      pp.info->launch(P, pp.grid, cs);
+    }
+  } else if (variant == V_POW2) {
     int rc = pow2_launch(st->pw, P, cs);
     if (rc) return failmsg(std::string("pow2 stage launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   } else if (st->d.prec == 8) {

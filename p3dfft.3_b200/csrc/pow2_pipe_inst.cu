@@ -1,0 +1,24 @@
+// pow2_pipe_inst.cu -- instantiates the pipelined stage kernels of ONE (precision, kind) pair; the Makefile compiles this
+// file eight times (-DPIPE_PREC=4|8 -DPIPE_KIND=1..4) so the instantiations build in parallel.
+#include "pow2_pipe.cuh"
+
+#if PIPE_PREC == 8
+#define PIPE_T double
+#else
+#define PIPE_T float
+#endif
+#define PIPE_CAT2(a, b, c) a##b##_##c
+#define PIPE_CAT(a, b, c) PIPE_CAT2(a, b, c)
+#define PIPE_FN PIPE_CAT(pipe_lookup_p, PIPE_PREC, PIPE_KIND)
+
+namespace p3b {
+
+const PipeInfo *PIPE_FN(int ld, int M, int P) {
+#if PIPE_KIND == 3  // P3DFFTCU_K_R2C: also the real-granule loader
+  if (ld == LD_REAL) return pipe_info<PIPE_T, PIPE_KIND, LD_REAL>(M, P);
+#endif
+  if (ld != LD_ELEM) return nullptr;
+  return pipe_info<PIPE_T, PIPE_KIND, LD_ELEM>(M, P);
+}
+
+}  // namespace p3b

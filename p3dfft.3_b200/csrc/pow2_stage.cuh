@@ -126,6 +126,9 @@ __device__ __forceinline__ void reg_pass(typename cx<T>::type *v, int t, int Ns,
   typedef typename cx<T>::type C;
   constexpr int TP = M / E;
   constexpr int NB = E / R;
+#ifdef P3B_SKELETON  // tools/microbench only: data movement without arithmetic, to find the ceiling of the access pattern
+  return;
+#endif
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     C a[R];

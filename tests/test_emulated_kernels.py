@@ -10,6 +10,20 @@ from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, h
 from util import TOL, check_golden, run_1d, run_3d
 
 
+def fast_variant(name):
+    """pipelined (pow2_pipe.cuh) or plain (pow2_stage.cuh) register-radix kernel, not the generic one"""
+    return name.startswith("pipe<") or name.startswith("pow2<")
+
+
+@pytest.fixture(params=["pipe", "nopipe"])
+def both_pow2_kernels(request, monkeypatch):
+    """run a test once with the pipelined kernel (default) and once with the plain pow2 kernel (the fallback for
+    unaligned pointers); the choice is read from the environment when a stage is created"""
+    if request.param == "nopipe":
+        monkeypatch.setenv("P3DFFT_B200_NO_PIPE", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("n", [(16, 12, 10), (8, 9, 7), (6, 5, 4), (30, 3, 14)])
 def test_r2c_c2r_generic(emu, orc, n):
     assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
@@ -34,30 +48,30 @@ def test_all_memory_order_pairs(emu, orc, mo1, mo2):
 
 
 @pytest.mark.parametrize("m", [64, 128, 256, 512, 1024, 2048, 4096])
-def test_pow2_c2c_sizes(emu, orc, m):
+def test_pow2_c2c_sizes(emu, orc, m, both_pow2_kernels):
     """every size of the register-radix fast path, transform dimension leading"""
     n = (m, 3, 2)
     err, out, want, desc = run_3d(emu, orc, n, n, ["CFFT_FORWARD_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"],
                                   (0, 1, 2), (0, 1, 2), return_all=True)
-    assert any("pow2" in s["variant"] for s in desc["stages"]), desc
+    assert any(fast_variant(s["variant"]) for s in desc["stages"]), desc
     assert err < TOL[8]
 
 
 @pytest.mark.parametrize("m", [128, 512, 2048])
-def test_pow2_real_sizes(emu, orc, m):
+def test_pow2_real_sizes(emu, orc, m, both_pow2_kernels):
     n = (m, 2, 3)
     err, _, _, desc = run_3d(emu, orc, n, half(n), ["R2CFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"], (0, 1, 2),
                              (0, 1, 2), cs2=0, return_all=True)
-    assert "pow2" in desc["stages"][0]["variant"]
+    assert fast_variant(desc["stages"][0]["variant"])
     assert err < TOL[8]
     err, _, _, desc = run_3d(emu, orc, half(n), n, ["C2RFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"], (0, 1, 2),
                              (0, 1, 2), cs1=0, return_all=True)
-    assert "pow2" in desc["stages"][-1]["variant"]
+    assert fast_variant(desc["stages"][-1]["variant"])
     assert err < TOL[8]
 
 
 @pytest.mark.parametrize("mo1,mo2", [((0, 1, 2), (1, 2, 0)), ((1, 2, 0), (0, 1, 2)), ((2, 1, 0), (1, 0, 2)), ((0, 2, 1), (2, 0, 1))])
-def test_pow2_strided_and_transposing(emu, orc, mo1, mo2):
+def test_pow2_strided_and_transposing(emu, orc, mo1, mo2, both_pow2_kernels):
     """fast path with the transform dimension not leading on one or both sides (64 and 128 points)"""
     n = (64, 128, 12)
     assert run_3d(emu, orc, n, n, CCC, mo1, mo2) < TOL[8]

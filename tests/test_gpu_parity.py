@@ -11,6 +11,14 @@ from util import TOL, check_golden, run_1d, run_3d
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["pipe", "nopipe"])
+def both_pow2_kernels(request, monkeypatch):
+    """pipelined kernel (default) and the plain pow2 kernel it falls back to for unaligned pointers"""
+    if request.param == "nopipe":
+        monkeypatch.setenv("P3DFFT_B200_NO_PIPE", "1")
+    return request.param
+
+
 def test_library_is_the_cuda_build(gpu):
     assert "sm_100a" in gpu.version()
     assert gpu.have_device()
@@ -33,7 +41,7 @@ def test_all_memory_order_pairs(gpu, orc, mo1, mo2):
 
 @pytest.mark.parametrize("m", [64, 128, 256, 512, 1024, 2048, 4096])
 @pytest.mark.parametrize("types", [CCC, CCC_B, CCC_S])
-def test_pow2_c2c_sizes(gpu, orc, m, types):
+def test_pow2_c2c_sizes(gpu, orc, m, types, both_pow2_kernels):
     n = (m, 24, 20)
     prec = 4 if types is CCC_S else 8
     for mo1, mo2 in (((0, 1, 2), (0, 1, 2)), ((1, 0, 2), (1, 0, 2)), ((0, 1, 2), (1, 2, 0)), ((2, 1, 0), (0, 2, 1))):
@@ -41,7 +49,7 @@ def test_pow2_c2c_sizes(gpu, orc, m, types):
 
 
 @pytest.mark.parametrize("m", [128, 256, 512, 1024, 2048, 4096])
-def test_pow2_real_sizes(gpu, orc, m):
+def test_pow2_real_sizes(gpu, orc, m, both_pow2_kernels):
     n = (m, 12, 10)
     for mo1, mo2 in (((0, 1, 2), (0, 1, 2)), ((0, 1, 2), (1, 2, 0)), ((1, 2, 0), (0, 1, 2)), ((2, 0, 1), (1, 0, 2))):
         assert run_3d(gpu, orc, n, half(n), RCC, mo1, mo2, cs2=0) < TOL[8]
