@@ -23,22 +23,22 @@
 using namespace p3b;
 
 namespace p3b {
-#define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int ld, int M, int P);
+#define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int lm, int M, int P);
 P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4)
 P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4)
 #undef P3B_DECL_PIPE
-const PipeInfo *pipe_lookup(int prec, int kind, int ld, int M, int P) {
+const PipeInfo *pipe_lookup(int prec, int kind, int lm, int M, int P) {
   if (prec == 4) switch (kind) {
-      case 1: return pipe_lookup_p4_1(ld, M, P);
-      case 2: return pipe_lookup_p4_2(ld, M, P);
-      case 3: return pipe_lookup_p4_3(ld, M, P);
-      case 4: return pipe_lookup_p4_4(ld, M, P);
+      case 1: return pipe_lookup_p4_1(lm, M, P);
+      case 2: return pipe_lookup_p4_2(lm, M, P);
+      case 3: return pipe_lookup_p4_3(lm, M, P);
+      case 4: return pipe_lookup_p4_4(lm, M, P);
     }
   if (prec == 8) switch (kind) {
-      case 1: return pipe_lookup_p8_1(ld, M, P);
-      case 2: return pipe_lookup_p8_2(ld, M, P);
-      case 3: return pipe_lookup_p8_3(ld, M, P);
-      case 4: return pipe_lookup_p8_4(ld, M, P);
+      case 1: return pipe_lookup_p8_1(lm, M, P);
+      case 2: return pipe_lookup_p8_2(lm, M, P);
+      case 3: return pipe_lookup_p8_3(lm, M, P);
+      case 4: return pipe_lookup_p8_4(lm, M, P);
     }
   return nullptr;
 }
@@ -290,40 +290,53 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
   int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
   const bool needU = fin == 1 || fout == 1, needV = fin == 2 || fout == 2;
-  int ld = LD_ELEM;
-  if (d.kind == P3DFFTCU_K_R2C && !(d.is_d == 1 && d.is_u % 2 == 0 && d.is_v % 2 == 0)) ld = LD_REAL;
-  const size_t esz = (size_t)d.prec * 2;
-  int want = (needU || needV) ? (int)(128 / esz) : 4;  // 128-byte runs across pencils when a side is transposed
-  if (ld == LD_REAL && fin != 0) want *= 2;           // runs of reals are half as long
-  if (needU && needV) want = 16;
+  if (needU && needV) return -1;  // 2-D tiles (input and output transposed along different dimensions): plain kernel
+  // bulk copies: 16-byte aligned rows.  esz = bytes of one input element
+  const long long esz = (long long)d.prec * d.dt_in;
+  int lm;
+  if (fin == 0) {
+    lm = LM_PENCIL;
+    if (d.is_d != 1 || (d.is_u * esz) % 16 || (d.is_v * esz) % 16 || ((long long)d.n_in * esz) % 16) return -1;
+  } else {
+    lm = LM_ROWS;
+    if (d.dt_in != 2) return -1;
+    const long long srun = fin == 1 ? d.is_u : d.is_v, sother = fin == 1 ? d.is_v : d.is_u, ext = fin == 1 ? d.nu : d.nv;
+    if (srun != 1 || (d.is_d * esz) % 16 || (sother * esz) % 16) return -1;
+    if (esz < 16 && ext % (16 / esz)) return -1;  // partial rows must stay multiples of 16 bytes
+  }
+  const size_t csz = (size_t)d.prec * 2;
+  int want = (needU || needV) ? (int)(128 / csz) : (M >= 1024 ? 1 : 2);  // 128-byte runs across pencils when a side is transposed
   if (const char *e = getenv("P3DFFT_B200_POW2_PENCILS")) {
     int w = atoi(e);
     if (w > 0) want = w;
   }
-  long long npen = d.nu * d.nv;
-  while (want > 2 && want / 2 >= npen) want /= 2;
+  const long long ext = needV ? d.nv : d.nu;
+  while (want > 1 && want / 2 >= ext) want /= 2;
   if (want > 16) want = 16;
   const PipeInfo *info = nullptr;
   int P = want;
-  for (; P >= 2; P /= 2) {
-    info = pipe_lookup(d.prec, d.kind, ld, M, P);
+  for (; P >= 1; P /= 2) {
+    info = pipe_lookup(d.prec, d.kind, lm, M, P);
     if (info && info->smem <= g_smem_optin) break;
     info = nullptr;
   }
+  if (!info) {  // small cores need several pencils to fill a warp
+    for (P = want * 2; P <= 16 && !info; P *= 2) {
+      info = pipe_lookup(d.prec, d.kind, lm, M, P);
+      if (info && info->smem > g_smem_optin) info = nullptr;
+      if (info) break;
+    }
+  }
   if (!info) return -1;
   int tu = P, tv = 1;
-  if (needU && needV) {
-    tu = 1;
-    while (tu * tu < P) tu *= 2;
-    tv = P / tu;
-  } else if (needV) {
+  if (needV) {
     tv = P;
     tu = 1;
   }
   pp->info = info;
   pp->M = M;
   pp->P = P;
-  pp->ld = ld;
+  pp->ld = lm;
   pp->tile_u = tu;
   pp->tile_v = tv;
   pp->tu_log2 = ilog2(tu);
@@ -338,8 +351,9 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   long long g = (long long)g_num_sms * occ;
   pp->grid = (int)(pp->ntiles < g ? (pp->ntiles > 0 ? pp->ntiles : 1) : g);
   char nm[220];
-  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,xs=%d,ld=%d> threads=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d occ=%d",
-           d.prec == 8 ? "f64" : "f32", M, P, info->xs, ld, info->threads, tu, tv, pp->load_ord, pp->store_ord, info->smem, pp->grid, occ);
+  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,xs=%d,%s> threads=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", M, P, info->xs, lm == LM_PENCIL ? "pencil" : "rows", info->threads, tu, tv, pp->load_ord,
+           pp->store_ord, info->smem, pp->grid, occ);
   *name = nm;
   return 0;
 }
@@ -495,9 +509,8 @@ int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int
   cudaStream_t cs = (cudaStream_t)stream;
   Variant variant = st->variant;
   if (variant == V_PIPE) {
-    // cp.async needs element-aligned sources; an odd user pointer takes the non-pipelined kernel instead
-    const size_t need = (size_t)st->d.prec * (st->pp.ld == LD_REAL ? 1 : 2);
-    if (((uintptr_t)in) % need) variant = st->have_pw ? V_POW2 : V_GENERIC;
+    // bulk copies need 16-byte aligned sources; an odd user pointer takes the non-pipelined kernel instead
+    if (((uintptr_t)in) % 16) variant = st->have_pw ? V_POW2 : V_GENERIC;
   }
   if (variant == V_PIPE) {
     const PipePlan &pp = st->pp;

@@ -13,12 +13,12 @@
 
 namespace p3b {
 
-const PipeInfo *PIPE_FN(int ld, int M, int P) {
-#if PIPE_KIND == 3  // P3DFFTCU_K_R2C: also the real-granule loader
-  if (ld == LD_REAL) return pipe_info<PIPE_T, PIPE_KIND, LD_REAL>(M, P);
+const PipeInfo *PIPE_FN(int lm, int M, int P) {
+#if PIPE_KIND != 3  // real input (R2C) is only staged pencil-major
+  if (lm == LM_ROWS) return pipe_info<PIPE_T, PIPE_KIND, LM_ROWS>(M, P);
 #endif
-  if (ld != LD_ELEM) return nullptr;
-  return pipe_info<PIPE_T, PIPE_KIND, LD_ELEM>(M, P);
+  if (lm != LM_PENCIL) return nullptr;
+  return pipe_info<PIPE_T, PIPE_KIND, LM_PENCIL>(M, P);
 }
 
 }  // namespace p3b

@@ -96,8 +96,9 @@ double stage_cost(int d, const int mo_in[3], const int ld_in[3], const int mo_ou
   int fi = lead_dim(mo_in, ld_in), fo = lead_dim(mo_out, ld_out);
   double c;
   if (fi == d && fo == d) c = 1.00;
-  else if (fi == fo) c = 1.05;
-  else if (fi == d || fo == d) c = 1.10;
+  else if (fi == fo) c = 1.30;  // row-granular loads AND stores (measured slowest: 128-byte bulk copies per row)
+  else if (fi == d) c = 1.08;  // contiguous (TMA-prefetched) loads + transposed stores: stores do not stall the pipeline
+  else if (fo == d) c = 1.12;  // transposed loads + contiguous stores
   else c = 1.60;
   if (mo_in[0] == mo_out[0] && mo_in[1] == mo_out[1] && mo_in[2] == mo_out[2]) c -= 0.02;
   return c;

@@ -31,6 +31,7 @@ extern thread_local emu_uint3 threadIdx;
 extern emu_uint3 blockIdx, blockDim, gridDim;
 extern pthread_barrier_t emu_block_barrier;
 inline void __syncthreads() { pthread_barrier_wait(&emu_block_barrier); }
+inline void __syncwarp() { pthread_barrier_wait(&emu_block_barrier); }  // callers are uniform across the CTA
 template <class T> inline T __ldg(const T *p) { return *p; }
 using std::max;
 using std::min;

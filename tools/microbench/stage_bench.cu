@@ -84,20 +84,36 @@ int main(int argc, char **argv) {
   {
     long long n = cbytes / 16;
     float ms = tm.run([&] { copy16<<<sms * 8, 512>>>((const double2 *)A, (double2 *)B, n); });
-    printf("copy16 contiguous                      %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e-3 * 1e3);
+    printf("copy16 contiguous                      %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
   }
   // y-stage pattern copies: rows of NXC complex, 1024 rows (y), NZ planes
   {
     float ms = tm.run([&] { tile_copy<8, 1024, 16><<<sms, 512>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
-    printf("tile_copy W=8  (128B runs) 512thr x1    %.3f ms  %.0f GB/s\n", ms, gb_c / ms);
+    printf("tile_copy W=8  (128B runs) 512thr x1    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
     ms = tm.run([&] { tile_copy<8, 1024, 16><<<sms * 2, 512>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
-    printf("tile_copy W=8  (128B runs) 512thr x2    %.3f ms  %.0f GB/s\n", ms, gb_c / ms);
+    printf("tile_copy W=8  (128B runs) 512thr x2    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
     ms = tm.run([&] { tile_copy<4, 1024, 16><<<sms * 4, 256>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
-    printf("tile_copy W=4  (64B runs)  256thr x4    %.3f ms  %.0f GB/s\n", ms, gb_c / ms);
+    printf("tile_copy W=4  (64B runs)  256thr x4    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
     ms = tm.run([&] { tile_copy<16, 1024, 16><<<sms, 1024>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
-    printf("tile_copy W=16 (256B runs) 1024thr x1   %.3f ms  %.0f GB/s\n", ms, gb_c / ms);
+    printf("tile_copy W=16 (256B runs) 1024thr x1   %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<2, 1024, 16><<<sms * 4, 128>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=2  (32B runs)  128thr x4    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<2, 1024, 16><<<sms * 8, 128>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=2  (32B runs)  128thr x8    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<1, 1024, 16><<<sms * 8, 64>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=1  (16B runs)  64thr x8     %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<1, 1024, 16><<<sms * 16, 64>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=1  (16B runs)  64thr x16    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<4, 1024, 16><<<sms * 2, 256>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=4  (64B runs)  256thr x2    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<4, 1024, 16><<<sms * 8, 256>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=4  (64B runs)  256thr x8    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<8, 1024, 16><<<sms * 4, 512>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
+    printf("tile_copy W=8  (128B runs) 512thr x4    %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
+    ms = tm.run([&] { tile_copy<8, 256, 16><<<sms * 16, 128>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ * 4, NXC * NY / 4); });
+    printf("tile_copy W=8 256 rows 128thr x16       %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
     ms = tm.run([&] { tile_copy<8, 1024, 8><<<sms * 2, 1024>>>((const double2 *)A, (double2 *)B, NXC, NXC - 1, NZ, NXC * NY); });
-    printf("tile_copy W=8 E=8 1024thr x2            %.3f ms  %.0f GB/s\n", ms, gb_c / ms);
+    printf("tile_copy W=8 E=8 1024thr x2            %.3f ms  %.0f GB/s\n", ms, gb_c / ms * 1e3);
   }
   // ---- stage kernels: y-stage forward (load U runs, store D contiguous): in mo 012 {NXC,NY,NZ} -> out mo 102 {NY,NXC,NZ}
   StageParams P;
@@ -118,9 +134,9 @@ int main(int argc, char **argv) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float ms = tm.run([&] { kern<<<sms * ctas, threads, smem>>>(P); });
     CK(cudaGetLastError());
-    printf("%-38s %.3f ms  %.0f GB/s\n", name, ms, gb_c / ms);
+    printf("%-38s %.3f ms  %.0f GB/s\n", name, ms, gb_c / ms * 1e3);
   };
-  if (N == 1024) {
+  if (N == 1024 && !(argc > 2)) {
     constexpr int M = 1024;
     size_t pen = (size_t)Pow2Smem<M>::PENCIL * 16;
     set_tiles(8, 1, ORD_U, ORD_D);
@@ -128,7 +144,7 @@ int main(int argc, char **argv) {
     set_tiles(4, 1, ORD_U, ORD_D);
     run_old(pow2_stage_kernel<double, M, 256, 2>, 256, 4 * pen, 2, "Yfwd old P=4 256thr x2");
     set_tiles(8, 1, ORD_U, ORD_D);
-    run_old(pow2_pipe_kernel<double, M, 1, 8, 0>, 512, PipeCfg<double, M, 8>::smem, 1, "Yfwd pipe P=8");
+    run_old(pow2_pipe_kernel<double, M, 1, 8, LM_ROWS>, 512, PipeCfg<double, M, 1, 8, LM_ROWS>::smem, 1, "Yfwd pipe rows P=8");
     // y-stage backward pattern: load D contiguous, store U runs: in {NY,NXC,NZ} mo 102 -> out mo 012
     P.is_d = 1; P.is_u = NY; P.is_v = NY * NXC;
     P.seg[0].os_d = NXC; P.seg[0].os_u = 1; P.seg[0].os_v = NXC * NY;
@@ -138,7 +154,7 @@ int main(int argc, char **argv) {
     set_tiles(4, 1, ORD_D, ORD_U);
     run_old(pow2_stage_kernel<double, M, 256, 2>, 256, 4 * pen, 2, "Ybwd old P=4 256thr x2");
     set_tiles(8, 1, ORD_D, ORD_U);
-    run_old(pow2_pipe_kernel<double, M, 1, 8, 0>, 512, PipeCfg<double, M, 8>::smem, 1, "Ybwd pipe P=8");
+    run_old(pow2_pipe_kernel<double, M, 1, 8, LM_PENCIL>, 512, PipeCfg<double, M, 1, 8, LM_PENCIL>::smem, 1, "Ybwd pipe pencil P=8");
     // contiguous both sides (in-place layout, like a 1D batched FFT)
     P.is_d = 1; P.is_u = NY; P.is_v = NY * NXC;
     P.seg[0].os_d = 1; P.seg[0].os_u = NY; P.seg[0].os_v = NY * NXC;
@@ -152,7 +168,11 @@ int main(int argc, char **argv) {
     set_tiles(1, 1, ORD_D, ORD_D);
     run_old(pow2_stage_kernel<double, M, 64, 8>, 64, 1 * pen, 8, "contig old P=1 64thr x8");
     set_tiles(4, 1, ORD_D, ORD_D);
-    run_old(pow2_pipe_kernel<double, M, 1, 4, 0>, 256, PipeCfg<double, M, 4>::smem, 1, "contig pipe P=4");
+    run_old(pow2_pipe_kernel<double, M, 1, 4, LM_PENCIL>, 256, PipeCfg<double, M, 1, 4, LM_PENCIL>::smem, 1, "contig pipe P=4 x1");
+    set_tiles(2, 1, ORD_D, ORD_D);
+    run_old(pow2_pipe_kernel<double, M, 1, 2, LM_PENCIL>, 128, PipeCfg<double, M, 1, 2, LM_PENCIL>::smem, 3, "contig pipe P=2 x3");
+    set_tiles(1, 1, ORD_D, ORD_D);
+    run_old(pow2_pipe_kernel<double, M, 1, 1, LM_PENCIL>, 64, PipeCfg<double, M, 1, 1, LM_PENCIL>::smem, 6, "contig pipe P=1 x6");
   }
   return 0;
 }
