@@ -7,8 +7,8 @@ PKG      := p3dfft.3_b200
 NVCC     := nvcc
 CXX      := g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-comment -Iinclude -Iinclude/compat -I$(PKG)/host
-NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -I$(PKG)/csrc
+CXXFLAGS := -O2 -std=c++17 -fPIC -fno-gnu-unique -Wall -Wno-comment -Iinclude -Iinclude/compat -I$(PKG)/host
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fno-gnu-unique -Iinclude -I$(PKG)/csrc
 HOSTSRC  := geometry registry planner executor cwrap minimpi
 OBJDIR   := $(PKG)/lib/obj
 HOSTOBJ  := $(HOSTSRC:%=$(OBJDIR)/%.o)
@@ -40,14 +40,14 @@ $(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(PIPEOBJ)
 emu: $(EMULIB)
 $(EMUDIR)/gpu_layer_emu.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
-	$(CXX) -O1 -std=c++17 -fPIC -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -c $< -o $@
+	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -c $< -o $@
 $(EMUDIR)/emu_globals.o: tools/cuda_emu/emu_globals.cpp tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
-	$(CXX) -O1 -std=c++17 -fPIC -Itools/cuda_emu -c $< -o $@
+	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -Itools/cuda_emu -c $< -o $@
 EMUPIPEOBJ := $(PIPEKEYS:%=$(EMUDIR)/pipe_%.o)
 $(EMUDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
-	$(CXX) -O1 -std=c++17 -fPIC -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
 $(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUPIPEOBJ)
 	$(CXX) -shared -o $@ $^ -lrt -lpthread
 

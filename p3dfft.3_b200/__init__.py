@@ -99,7 +99,7 @@ class Library:
                 f"{path} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
                 "There is no fallback implementation.")
         self.path = path
-        self.dll = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        self.dll = ctypes.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_DEEPBIND)  # product and emulation builds define the same symbols
         d = self.dll
         d.p3dfft_init_data_grid.restype = POINTER(Grid)
         d.p3dfft_b200_version.restype = c_char_p
