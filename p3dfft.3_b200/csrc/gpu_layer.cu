@@ -23,22 +23,22 @@
 using namespace p3b;
 
 namespace p3b {
-#define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int lm, int M, int P);
+#define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int ts, int M, int P);
 P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4)
 P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4)
 #undef P3B_DECL_PIPE
-const PipeInfo *pipe_lookup(int prec, int kind, int lm, int M, int P) {
+const PipeInfo *pipe_lookup(int prec, int kind, int ts, int M, int P) {
   if (prec == 4) switch (kind) {
-      case 1: return pipe_lookup_p4_1(lm, M, P);
-      case 2: return pipe_lookup_p4_2(lm, M, P);
-      case 3: return pipe_lookup_p4_3(lm, M, P);
-      case 4: return pipe_lookup_p4_4(lm, M, P);
+      case 1: return pipe_lookup_p4_1(ts, M, P);
+      case 2: return pipe_lookup_p4_2(ts, M, P);
+      case 3: return pipe_lookup_p4_3(ts, M, P);
+      case 4: return pipe_lookup_p4_4(ts, M, P);
     }
   if (prec == 8) switch (kind) {
-      case 1: return pipe_lookup_p8_1(lm, M, P);
-      case 2: return pipe_lookup_p8_2(lm, M, P);
-      case 3: return pipe_lookup_p8_3(lm, M, P);
-      case 4: return pipe_lookup_p8_4(lm, M, P);
+      case 1: return pipe_lookup_p8_1(ts, M, P);
+      case 2: return pipe_lookup_p8_2(ts, M, P);
+      case 3: return pipe_lookup_p8_3(ts, M, P);
+      case 4: return pipe_lookup_p8_4(ts, M, P);
     }
   return nullptr;
 }
@@ -289,58 +289,50 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   const int M = real ? d.nfft / 2 : d.nfft;
   int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
   int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
-  const bool needU = fin == 1 || fout == 1, needV = fin == 2 || fout == 2;
-  if (needU && needV) return -1;  // 2-D tiles (input and output transposed along different dimensions): plain kernel
-  // bulk copies: 16-byte aligned rows.  esz = bytes of one input element
+  if (fin != 0 || d.is_d != 1) return -1;  // bulk copies move whole pencils: the transform dimension must be unit-stride
+  // 16-byte aligned pencils of a multiple of 16 bytes.  esz = bytes of one input element
   const long long esz = (long long)d.prec * d.dt_in;
-  int lm;
-  if (fin == 0) {
-    lm = LM_PENCIL;
-    if (d.is_d != 1 || (d.is_u * esz) % 16 || (d.is_v * esz) % 16 || ((long long)d.n_in * esz) % 16) return -1;
-  } else {
-    lm = LM_ROWS;
-    if (d.dt_in != 2) return -1;
-    const long long srun = fin == 1 ? d.is_u : d.is_v, sother = fin == 1 ? d.is_v : d.is_u, ext = fin == 1 ? d.nu : d.nv;
-    if (srun != 1 || (d.is_d * esz) % 16 || (sother * esz) % 16) return -1;
-    if (esz < 16 && ext % (16 / esz)) return -1;  // partial rows must stay multiples of 16 bytes
-  }
+  if ((d.is_u * esz) % 16 || (d.is_v * esz) % 16 || ((long long)d.n_in * esz) % 16) return -1;
+  const int ts = fout != 0;
   const size_t csz = (size_t)d.prec * 2;
-  int want = (needU || needV) ? (int)(128 / csz) : (M >= 1024 ? 1 : 2);  // 128-byte runs across pencils when a side is transposed
-  if (const char *e = getenv("P3DFFT_B200_POW2_PENCILS")) {
+  const int E = M == 64 ? 8 : 16, TP = M / E;
+  // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
+  int want = ts ? (int)(128 / csz) : (256 / TP > 0 ? 256 / TP : 1);
+  if (const char *e = getenv(ts ? "P3DFFT_B200_POW2_PENCILS" : "P3DFFT_B200_POW2_PENCILS_PM")) {
     int w = atoi(e);
     if (w > 0) want = w;
   }
-  const long long ext = needV ? d.nv : d.nu;
+  const long long ext = fout == 2 ? d.nv : d.nu;
   while (want > 1 && want / 2 >= ext) want /= 2;
   if (want > 16) want = 16;
   const PipeInfo *info = nullptr;
   int P = want;
   for (; P >= 1; P /= 2) {
-    info = pipe_lookup(d.prec, d.kind, lm, M, P);
+    info = pipe_lookup(d.prec, d.kind, ts, M, P);
     if (info && info->smem <= g_smem_optin) break;
     info = nullptr;
   }
   if (!info) {  // small cores need several pencils to fill a warp
     for (P = want * 2; P <= 16 && !info; P *= 2) {
-      info = pipe_lookup(d.prec, d.kind, lm, M, P);
+      info = pipe_lookup(d.prec, d.kind, ts, M, P);
       if (info && info->smem > g_smem_optin) info = nullptr;
       if (info) break;
     }
   }
   if (!info) return -1;
   int tu = P, tv = 1;
-  if (needV) {
+  if (fout == 2) {
     tv = P;
     tu = 1;
   }
   pp->info = info;
   pp->M = M;
   pp->P = P;
-  pp->ld = lm;
+  pp->ld = ts;
   pp->tile_u = tu;
   pp->tile_v = tv;
   pp->tu_log2 = ilog2(tu);
-  pp->load_ord = fin == 0 ? ORD_D : (fin == 1 ? ORD_U : ORD_V);
+  pp->load_ord = ORD_D;
   pp->store_ord = fout == 0 ? ORD_D : (fout == 1 ? ORD_U : ORD_V);
   pp->tiles_u = (d.nu + tu - 1) / tu;
   pp->ntiles = pp->tiles_u * ((d.nv + tv - 1) / tv);
@@ -351,9 +343,9 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   long long g = (long long)g_num_sms * occ;
   pp->grid = (int)(pp->ntiles < g ? (pp->ntiles > 0 ? pp->ntiles : 1) : g);
   char nm[220];
-  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,xs=%d,%s> threads=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d occ=%d",
-           d.prec == 8 ? "f64" : "f32", M, P, info->xs, lm == LM_PENCIL ? "pencil" : "rows", info->threads, tu, tv, pp->load_ord,
-           pp->store_ord, info->smem, pp->grid, occ);
+  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s> threads=%d tile=%dx%d store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", info->threads, tu, tv, pp->store_ord, info->smem,
+           pp->grid, occ);
   *name = nm;
   return 0;
 }

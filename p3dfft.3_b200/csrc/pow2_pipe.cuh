@@ -1,24 +1,24 @@
-// pow2_pipe.cuh -- TMA-fed, software-pipelined stage kernel for power-of-two FFT cores (the production fast path).
+// pow2_pipe.cuh -- TMA-fed stage kernel for power-of-two FFT cores with unit-stride input (the production fast path).
 //
 // Same arithmetic as pow2_stage.cuh (register-resident radix-16/8/4/2 Stockham passes, E complex values per
-// thread, padded shared-memory exchanges, R2C/C2R through the half-length complex core) but restructured so
-// that HBM traffic and arithmetic overlap inside one resident CTA:
-//   * a persistent CTA walks its tiles of P pencils; while tile i is being transformed, tile i+1 streams from
-//     global memory into the staging buffer S through the TMA unit (cp.async.bulk -> UBLKCP) and signals an
-//     mbarrier: no registers, no LSU wavefronts and no per-element address arithmetic are spent on loads.
-//       LM_PENCIL  transform dimension is unit-stride: one bulk copy per pencil, S is pencil-major
-//       LM_ROWS    pencils are adjacent in memory (transposed input): one bulk copy per row of P elements,
-//                  S is row-major with pitch P+1 so that the column reads below are bank-conflict free
-//   * at the top of an iteration the tile is read out of S into registers (one LDS per value, applying the
-//     kind's pre-processing), S is released and the bulk copies of the next tile are issued at once, so a
-//     full tile of loads is in flight during all the passes, exchanges and stores of the current tile;
-//   * passes exchange through a second buffer X; when S + X do not fit in 227 KB (1024-point double with 8
-//     pencils) two pencils share one X region and take turns; the barriers of an exchange only span the
-//     threads that share a region (named barriers), so different pencils of a tile drift apart and their
-//     shared-memory and FP64 phases overlap;
-//   * stores go straight from registers to global (or to a peer's buffer over NVLink through the segment
-//     table) in the OUTPUT's coalescing order: the thread -> (pencil, slot) mapping is chosen for the store side.
-// Bulk copies need 16-byte aligned rows; the host selects this kernel only then (pow2_stage.cuh otherwise).
+// thread, R2C/C2R through the half-length complex core).  Data movement:
+//   * one shared-memory buffer per pencil, used IN PLACE: the pencil lands there by one bulk copy (cp.async.bulk ->
+//     UBLKCP, completion on the pencil's own mbarrier: no registers, LSU wavefronts or address arithmetic are spent
+//     on loads), is read into registers, and the same buffer then carries the padded Stockham exchanges (a pencil is
+//     entirely in registers between passes, so nothing is lost by overwriting it);
+//   * as soon as the last exchange of a tile has been read back, the pencil's leader thread issues the bulk copy of
+//     the NEXT tile's pencil into the buffer, so the load is in flight during the last pass, the epilogue and all the
+//     global stores of the current tile;
+//   * contiguous output (TS = 0): the TP threads of a pencil form an independent group -- group-scoped named barriers
+//     only, groups of one CTA drift apart, so their load, shared-memory, FP64 and store phases overlap;
+//   * transposed output (TS = 1): the last exchange re-maps threads from (pencil-major) to (lanes across the tile's P
+//     pencils), so the stores -- straight from registers to global memory, or to a peer's buffer over NVLink through
+//     the segment table -- are runs of P elements along the OUTPUT's unit-stride dimension; only that exchange and
+//     what follows it synchronise the whole CTA;
+//   * twiddles of passes 2 and 3 come from compact shared-memory tables laid out [q][k] so that a warp's reads are
+//     contiguous.
+// Bulk copies need 16-byte aligned pencils; the host selects this kernel only then (pow2_stage.cuh otherwise, which
+// also serves inputs whose unit-stride direction is not the transform dimension).
 // Replaces reference FFTW execute + reorder_trans + pack_sendbuf_trans (exec.C:737-1326, 2792-2879).
 #pragma once
 #include "common.cuh"
@@ -26,8 +26,6 @@
 #include "pow2_stage.cuh"
 
 namespace p3b {
-
-enum { LM_PENCIL = 0, LM_ROWS = 1 };
 
 // ------------------------------------------------------------------ mbarrier / bulk-copy wrappers
 #ifdef P3B_EMU
@@ -75,31 +73,22 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) { asm volatile("
 
 constexpr size_t kPipeSmemMax = 232448 - 1024;  // 227 KB opt-in minus the static reserve
 
-template <typename T, int M, int KIND, int P, int LM> struct PipeCfg {
-  enum { E = Pow2Cfg<M>::E, TP = M / E, THREADS = P * TP, XPITCH = Pow2Smem<M>::PENCIL };
-  enum { NIN = KIND == P3DFFTCU_K_C2R ? M + 1 : M };          // complex-sized elements per pencil in S
+template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
+  enum { E = Pow2Cfg<M>::E, TP = M / E, THREADS = P * TP, XP0 = Pow2Smem<M>::PENCIL };
+  enum { R1 = Pow2Cfg<M>::R1, R2 = Pow2Cfg<M>::R2, R3 = Pow2Cfg<M>::R3 };
+  enum { NIN = KIND == P3DFFTCU_K_C2R ? M + 1 : M };  // complex-sized elements of one pencil landing in shared memory
   static constexpr size_t csz = 2 * sizeof(T);
-  // S pitch: every pencil (LM_PENCIL) or row (LM_ROWS) starts 16-byte aligned for the bulk copies and an odd number of
-  // 16-byte units after the previous one, which spreads the strided reads of the compute mapping over the banks
-  static constexpr int span_units = (int)(((LM == LM_PENCIL ? NIN : P) * csz + 15) / 16);
-  enum { SPITCH = (int)(((span_units % 2 == 0 ? span_units + 1 : span_units + 2) * 16) / csz) };
-  static constexpr size_t s_bytes = (LM == LM_PENCIL ? (size_t)P * SPITCH : (size_t)NIN * SPITCH) * csz;
-  static constexpr size_t x_pencil = (size_t)XPITCH * csz;
-  // compact twiddle tables kept in shared memory: with ~200 KB of it in use the L1 that is left cannot hold the
-  // global table, and a miss on the critical path of every pass costs an L2 round trip
-  // (with little shared memory in use the L1 holds the global table and plain __ldg loads are cheaper: TW_SMEM = 0)
-  static constexpr bool TW_SMEM = s_bytes + (P / 2) * x_pencil > 100 * 1024;
-  enum { T2N = TW_SMEM ? Pow2Cfg<M>::R1 * Pow2Cfg<M>::R2 : 0, T3N = (TW_SMEM && Pow2Cfg<M>::R3 > 1) ? TP * Pow2Cfg<M>::R3 : 0 };
-  static constexpr size_t t_bytes = (size_t)(T2N + T3N) * csz;
-  static constexpr bool fits1 = s_bytes + P * x_pencil + t_bytes + 64 <= kPipeSmemMax;
-  static constexpr bool fits2 = (P >= 2) && s_bytes + (P / 2) * x_pencil + t_bytes + 64 <= kPipeSmemMax;
-  static constexpr bool valid = (THREADS >= 32) && (THREADS <= 1024) && (fits1 || fits2);
-  enum { XS = fits1 ? 1 : 2, PX = P / XS };
-  static constexpr size_t smem = s_bytes + (size_t)PX * x_pencil + t_bytes + 64;
+  // pencil pitch (complex elements): every pencil starts 16-byte aligned (bulk-copy destination) an odd number of
+  // 16-byte units after the previous one, so the lanes-across-pencils accesses of the transposed mapping spread over
+  // the banks; XP0 = M + M/16 + 1 is odd
+  enum { PITCH = sizeof(T) == 8 ? XP0 : ((XP0 + 1) % 4 == 2 ? XP0 + 1 : XP0 + 3) };
+  enum { T2N = R1 * R2, T3N = R3 > 1 ? R3 * TP : 0 };
+  static constexpr size_t bar_bytes = 128;
+  static constexpr size_t smem = bar_bytes + ((size_t)P * PITCH + T2N + T3N) * csz;
+  static constexpr bool valid = (THREADS >= 32) && (THREADS <= 1024) && (P <= 16) && (smem <= kPipeSmemMax) && (TS ? P >= 2 : true) &&
+                                (TP > 32 ? P <= 15 : true);
   // register budget as in pow2_stage.cuh: 128 per thread in double, 80 in single
   enum { BUDGET = sizeof(T) == 8 ? 512 : 768, MINB = (BUDGET / THREADS) < 1 ? 1 : (BUDGET / THREADS) };
-  // an exchange region is shared by XS pencils; their threads form a barrier group when they are whole warps
-  enum { GROUP = XS * TP, GROUPED = (TP % 32 == 0) && (P / XS <= 15) };
 };
 
 // a * exp(-2 pi i m / 16) for a compile-time m (folds to the cheapest form after unrolling)
@@ -126,7 +115,7 @@ template <typename T, typename C> __device__ __forceinline__ C mul_w16(C a, int 
   }
 }
 
-// second pass (Ns = R1): twiddle of butterfly input q is T2[k][q], k = j mod R1
+// second pass (Ns = R1): the twiddle of butterfly input q is T2[q][k], k = j mod R1
 template <typename T, int M, int E, int R1, int R>
 __device__ __forceinline__ void reg_pass2(typename cx<T>::type *v, int t, const typename cx<T>::type *T2) {
   typedef typename cx<T>::type C;
@@ -137,30 +126,30 @@ __device__ __forceinline__ void reg_pass2(typename cx<T>::type *v, int t, const 
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     C a[R];
-    const C *row = T2 + ((t + b * TP) & (R1 - 1)) * R;
+    const C *col = T2 + ((t + b * TP) & (R1 - 1));
 #pragma unroll
     for (int q = 0; q < R; q++) a[q] = v[b + q * NB];
 #pragma unroll
-    for (int q = 1; q < R; q++) a[q] = cmul(a[q], row[q]);
+    for (int q = 1; q < R; q++) a[q] = cmul(a[q], col[q * R1]);
     Radix<T, R>::run(a);
 #pragma unroll
     for (int q = 0; q < R; q++) v[b + q * NB] = a[q];
   }
 }
 
-// third pass (Ns * R = M): the twiddle w_M^{q (t + b TP)} factors into T3[t][q] and the 16th root w_16^{q b}
+// third pass (Ns * R = M): the twiddle w_M^{q (t + b TP)} factors into T3[q][t] and the 16th root w_16^{q b}
 // (TP = M / 16), so one small table serves all NB butterflies of a thread
 template <typename T, int M, int E, int R>
 __device__ __forceinline__ void reg_pass3(typename cx<T>::type *v, int t, const typename cx<T>::type *T3) {
   typedef typename cx<T>::type C;
-  constexpr int NB = E / R;
+  constexpr int TP = M / E, NB = E / R;
   static_assert(E == 16, "third pass assumes 16 values per thread");
 #ifdef P3B_SKELETON
   return;
 #endif
   C w[R];
 #pragma unroll
-  for (int q = 1; q < R; q++) w[q] = T3[t * R + q];
+  for (int q = 1; q < R; q++) w[q] = T3[q * TP + t];
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     C a[R];
@@ -175,108 +164,80 @@ __device__ __forceinline__ void reg_pass3(typename cx<T>::type *v, int t, const 
 }
 
 // ------------------------------------------------------------------ the kernel
-template <typename T, int M, int KIND, int P, int LM>
-__global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, LM>::THREADS, PipeCfg<T, M, KIND, P, LM>::MINB)
+template <typename T, int M, int KIND, int P, int TS>
+__global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, TS>::THREADS, PipeCfg<T, M, KIND, P, TS>::MINB)
 pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   typedef typename cx<T>::type C;
-  typedef PipeCfg<T, M, KIND, P, LM> Cfg;
-  typedef Pow2Cfg<M> R;
-  constexpr int E = R::E, R1 = R::R1, R2 = R::R2, R3 = R::R3;
-  constexpr int TP = Cfg::TP, THREADS = Cfg::THREADS, XPITCH = Cfg::XPITCH, SPITCH = Cfg::SPITCH, XS = Cfg::XS, PX = Cfg::PX;
-  constexpr int NIN = Cfg::NIN;
+  typedef PipeCfg<T, M, KIND, P, TS> Cfg;
+  constexpr int E = Cfg::E, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
+  constexpr int TP = Cfg::TP, THREADS = Cfg::THREADS, PITCH = Cfg::PITCH;
   constexpr bool r2c = KIND == P3DFFTCU_K_R2C, c2r = KIND == P3DFFTCU_K_C2R;
   constexpr bool bwd = KIND == P3DFFTCU_K_C2C_BWD || c2r;
   constexpr int twscale = (r2c || c2r) ? 2 : 1;  // the table is exp(-2 pi i j / nfft), nfft = 2M in the real cases
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw);  // mbarrier: tile landed in S
-  C *S = reinterpret_cast<C *>(smem_raw + 64);
-  C *X = reinterpret_cast<C *>(smem_raw + 64 + Cfg::s_bytes);
-  C *T2 = X + PX * XPITCH;    // [R1][R2]
-  C *T3 = T2 + Cfg::T2N;      // [TP][R3]
+  constexpr unsigned bytes = (unsigned)(Cfg::NIN * Cfg::csz);  // one pencil (R2C: 2M reals = M complex-sized elements)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);  // one mbarrier per pencil: "landed"
+  C *B = reinterpret_cast<C *>(smem_raw + Cfg::bar_bytes);
+  C *T2 = B + P * PITCH;   // [R2][R1]
+  C *T3 = T2 + Cfg::T2N;   // [R3][TP]
   const C *__restrict__ tw = (const C *)Q.tw;
   const int tid = threadIdx.x;
   const int tile_u = Q.tile_u, tu_log2 = Q.tu_log2;
-  for (int i = tid; i < Cfg::T2N; i += THREADS) T2[i] = tw[(i % R2) * (i / R2) * (M / (R1 * R2)) * twscale];
-  for (int i = tid; i < Cfg::T3N; i += THREADS) T3[i] = tw[(i % R3) * (i / R3) * twscale];
+  for (int i = tid; i < Cfg::T2N; i += THREADS) T2[i] = tw[(i / R1) * (i % R1) * (M / (R1 * R2)) * twscale];
+  for (int i = tid; i < Cfg::T3N; i += THREADS) T3[i] = tw[(i / TP) * (i % TP) * twscale];
 
-  // compute/store mapping: thread -> (pencil slot in tile, FFT slot t).  slot = pv * tile_u + pu
-  int slot, t;
-  const bool pencil_major = Q.store_ord == ORD_D;
-  if (pencil_major) { slot = tid / TP; t = tid % TP; }
-  else { slot = tid % P; t = tid / P; }  // 1-D tiles: the lanes run across the tile's pencils
-  const int pu = slot & (tile_u - 1), pv = slot >> tu_log2;
-  C *Xp = X + (slot % PX) * XPITCH;
-  const int xh = slot / PX;  // turn of this pencil in an exchange region shared by XS pencils
-  // barrier scope of an exchange: the threads sharing an X region when they are whole warps, else the CTA
-  const bool grouped = Cfg::GROUPED && pencil_major;
-  const int bar_id = 1 + (slot % PX);
-  auto xsync = [&]() {
-    if (grouped) {
-      if (Cfg::GROUP <= 32) __syncwarp();
-      else group_bar(bar_id, Cfg::GROUP);
-    } else __syncthreads();
+  // mapping A (load side and all passes but the last): pencil-major.  mapping B (last pass and stores): the same when
+  // the output is contiguous along the transform dimension, else the lanes run across the tile's pencils
+  const int slotA = tid / TP, tA = tid % TP;
+  const int slotB = TS ? tid % P : slotA, tB = TS ? tid / P : tA;
+  const int puA = slotA & (tile_u - 1), pvA = slotA >> tu_log2;
+  const int puB = slotB & (tile_u - 1), pvB = slotB >> tu_log2;
+  C *BA = B + slotA * PITCH, *BB = B + slotB * PITCH;
+  unsigned long long *bar = bars + slotA;
+  auto syncA = [&]() {  // the threads of one pencil (whole warps, or a fraction of one warp)
+    if (TP <= 32) __syncwarp();
+    else group_bar(1 + slotA, TP);
   };
-
-  if (tid == 0) mbar_init(full, 1);
-  __syncthreads();
-
-  // bulk copies of one tile into S (TMA); every thread issues its share, thread 0 announces the byte count
-  auto prefetch = [&](long long tile) {
-    const long long u0 = (tile % Q.tiles_u) * tile_u, v0 = (tile / Q.tiles_u) * Q.tile_v;
-    const int cu = (int)min((long long)tile_u, Q.nu - u0), cv = (int)min((long long)Q.tile_v, Q.nv - v0);
-    fence_async_smem();
-    if (LM == LM_PENCIL) {
-      constexpr unsigned bytes = (unsigned)(NIN * Cfg::csz);  // R2C: 2M reals = M complex-sized elements
-      if (tid == 0) mbar_expect_tx(full, bytes * (unsigned)(cu * cv));
-      if (tid < P) {
-        const int lu = tid & (tile_u - 1), lv = tid >> tu_log2;
-        if (lu < cu && lv < cv) {
-          const long long base = (u0 + lu) * Q.is_u + (v0 + lv) * Q.is_v;
-          const void *src = r2c ? (const void *)((const T *)Q.in + base) : (const void *)((const C *)Q.in + base);
-          bulk_g2s(S + tid * SPITCH, src, bytes, full);
-        }
+  auto syncB = [&]() {
+    if (TS) __syncthreads();
+    else syncA();
+  };
+  // the pencil's leader thread starts the bulk copy of its pencil of tile `tl`; a pencil outside the array completes
+  // the phase with zero bytes so that the waits stay uniform
+  auto issue = [&](long long tl) {
+    if (tA == 0 && tl < Q.ntiles) {
+      const long long u = (tl % Q.tiles_u) * tile_u + puA, v = (tl / Q.tiles_u) * Q.tile_v + pvA;
+      const bool live = u < Q.nu && v < Q.nv;
+      fence_async_smem();
+      mbar_expect_tx(bar, live ? bytes : 0u);
+      if (live) {
+        const long long base = u * Q.is_u + v * Q.is_v;
+        const void *src = r2c ? (const void *)((const T *)Q.in + base) : (const void *)((const C *)Q.in + base);
+        bulk_g2s(BA, src, bytes, bar);
       }
-    } else {
-      // rows of `w` adjacent pencils; the tile is 1-D (tile_u == P or tile_v == P)
-      const int w = cu * cv;
-      const unsigned bytes = (unsigned)(w * Cfg::csz);
-      if (tid == 0) mbar_expect_tx(full, bytes * (unsigned)NIN);
-      const C *src = (const C *)Q.in + u0 * Q.is_u + v0 * Q.is_v;
-      for (int j = tid; j < NIN; j += THREADS) bulk_g2s(S + j * SPITCH, src + (long long)j * Q.is_d, bytes, full);
     }
   };
-  // element j of this thread's pencil in S
-  auto s_at = [&](int j) -> C { return LM == LM_PENCIL ? S[slot * SPITCH + j] : S[j * SPITCH + slot]; };
 
-  // one exchange through X: scatter in Stockham order, gather in slot order; pencils sharing a region take turns
-  auto exchange = [&](C *v, auto scatter, bool lead_sync) {
-#pragma unroll
-    for (int h = 0; h < XS; h++) {
-      if (h > 0 || lead_sync) xsync();  // the region is free again
-      if (XS == 1 || xh == h) scatter(v);
-      xsync();
-      if (XS == 1 || xh == h) smem_gather<T, M, E>(v, Xp, t);
-    }
-  };
+  if (tid < P) mbar_init(bars + tid, 1);
+  __syncthreads();
 
   long long tile = blockIdx.x;
   unsigned parity = 0;
-  if (tile < Q.ntiles) prefetch(tile);
+  issue(tile);
   for (; tile < Q.ntiles; tile += gridDim.x) {
-    const long long u0 = (tile % Q.tiles_u) * tile_u, v0 = (tile / Q.tiles_u) * Q.tile_v;
-    const long long uo = u0 + pu, vo = v0 + pv;
+    const long long uo = (tile % Q.tiles_u) * tile_u + puB, vo = (tile / Q.tiles_u) * Q.tile_v + pvB;
     const bool live = uo < Q.nu && vo < Q.nv;
     C v[E];
-    mbar_wait(full, parity);  // the whole tile has landed in S
+    mbar_wait(bar, parity);  // this thread's pencil (mapping A) has landed
     parity ^= 1;
-    // ---------------- S -> registers (+ pre-processing)
+    // ---------------- shared memory -> registers (+ pre-processing)
     if (c2r) {
       // Z[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/N} (X[k] - conj X[M-k]); we need conj Z for the conj-trick inverse
 #pragma unroll
       for (int m = 0; m < E; m++) {
-        const int k = t + m * TP;
-        C a = s_at(k);
-        C b = cconj(s_at(M - k));
+        const int k = tA + m * TP;
+        C a = BA[k];
+        C b = cconj(BA[M - k]);
         if (k == 0) { a.y = 0; b.y = 0; }  // FFTW's c2r ignores Im X[0] and Im X[N/2]
         C s = cadd(a, b), d = csub(a, b);
         C w = cconj(__ldg(&tw[k]));
@@ -286,48 +247,56 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
     } else {
 #pragma unroll
       for (int m = 0; m < E; m++) {
-        C x = s_at(t + m * TP);
+        C x = BA[tA + m * TP];
         v[m] = bwd ? cconj(x) : x;
       }
     }
-    __syncthreads();  // everyone has read S: release it to the next tile
-    if (tile + gridDim.x < Q.ntiles) prefetch(tile + gridDim.x);
+    syncA();  // the pencil is in registers: its buffer now carries the exchanges
 
     // ---------------- passes
-    reg_pass<T, M, E, R1, false>(v, t, 1, tw, twscale);
-    exchange(v, [&](C *w) { smem_scatter<T, M, E, R1>(w, Xp, t, 1); }, false);  // X idle since the CTA barrier above
-    if constexpr (Cfg::TW_SMEM) reg_pass2<T, M, E, R1, R2>(v, t, T2);
-    else reg_pass<T, M, E, R2, true>(v, t, R1, tw, twscale);
+    reg_pass<T, M, E, R1, false>(v, tA, 1, tw, twscale);
+    smem_scatter<T, M, E, R1>(v, BA, tA, 1);
     if constexpr (R3 > 1) {
-      exchange(v, [&](C *w) { smem_scatter<T, M, E, R2>(w, Xp, t, R1); }, true);
-      if constexpr (Cfg::TW_SMEM) reg_pass3<T, M, E, R3>(v, t, T3);
-      else reg_pass<T, M, E, R3, true>(v, t, R1 * R2, tw, twscale);
+      syncA();
+      smem_gather<T, M, E>(v, BA, tA);
+      reg_pass2<T, M, E, R1, R2>(v, tA, T2);
+      syncA();
+      smem_scatter<T, M, E, R2>(v, BA, tA, R1);
     }
-    // v[m] = forward core output F[t + m*TP] of this thread's pencil
+    syncB();
+    smem_gather<T, M, E>(v, BB, tB);  // re-maps to the store side when TS
+    if constexpr (!r2c) {
+      syncB();  // every value is back in registers: the buffers are free for the next tile
+      issue(tile + gridDim.x);
+    }
+    if constexpr (R3 > 1) reg_pass3<T, M, E, R3>(v, tB, T3);
+    else reg_pass2<T, M, E, R1, R2>(v, tB, T2);
+    // v[m] = forward core output F[tB + m*TP] of pencil slotB
 
     // ---------------- epilogue + stores
-    if (r2c) {
+    if constexpr (r2c) {
       // X[k] = ((Z[k] + conj Z[M-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[M-k])) / 2, k = 0..M
+      syncB();
 #pragma unroll
-      for (int h = 0; h < XS; h++) {
-        xsync();  // the region is free
-        if (XS == 1 || xh == h) {
+      for (int m = 0; m < E; m++) BB[padidx(tB + m * TP)] = v[m];
+      syncB();
+      C xM = mk<T>((T)0, (T)0);
 #pragma unroll
-          for (int m = 0; m < E; m++) Xp[padidx(t + m * TP)] = v[m];
-        }
-        xsync();
-        if ((XS == 1 || xh == h) && live) {
+      for (int m = 0; m < E; m++) {
+        const int k = tB + m * TP;
+        const C zk = v[m];
+        const C zm = cconj(BB[padidx((M - k) & (M - 1))]);
+        C s = cadd(zk, zm), d = csub(zk, zm);
+        C e = cmulmi(cmul(d, __ldg(&tw[k])));
+        v[m] = mk<T>((T)0.5 * (s.x + e.x), (T)0.5 * (s.y + e.y));
+        if (m == 0) xM = mk<T>(zk.x - zk.y, (T)0);  // X[M], used by the thread that owns k = 0
+      }
+      syncB();
+      issue(tile + gridDim.x);
+      if (live) {
 #pragma unroll
-          for (int m = 0; m < E; m++) {
-            const int k = t + m * TP;
-            const C zk = v[m];
-            const C zm = cconj(Xp[padidx((M - k) & (M - 1))]);
-            C s = cadd(zk, zm), d = csub(zk, zm);
-            C e = cmulmi(cmul(d, __ldg(&tw[k])));
-            store_out<T>(Q, k, uo, vo, mk<T>((T)0.5 * (s.x + e.x), (T)0.5 * (s.y + e.y)));
-            if (k == 0) store_out<T>(Q, M, uo, vo, mk<T>(zk.x - zk.y, (T)0));
-          }
-        }
+        for (int m = 0; m < E; m++) store_out<T>(Q, tB + m * TP, uo, vo, v[m]);
+        if (tB == 0) store_out<T>(Q, M, uo, vo, xM);
       }
     } else if (c2r) {
       if (live) {  // conj(F(conj Z))[j] = x[2j] + i x[2j+1]; real output is never exchanged: one segment
@@ -336,11 +305,11 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         if (sg.os_d == 1 && (((uintptr_t)out) & (sizeof(C) - 1)) == 0) {
           C *oc = (C *)out;
 #pragma unroll
-          for (int m = 0; m < E; m++) oc[t + m * TP] = cconj(v[m]);
+          for (int m = 0; m < E; m++) oc[tB + m * TP] = cconj(v[m]);
         } else {
 #pragma unroll
           for (int m = 0; m < E; m++) {
-            long long a = (long long)(2 * (t + m * TP)) * sg.os_d;
+            long long a = (long long)(2 * (tB + m * TP)) * sg.os_d;
             out[a] = v[m].x;
             out[a + sg.os_d] = -v[m].y;
           }
@@ -349,67 +318,67 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
     } else if (live) {
       if (Q.nseg == 1 && Q.deriv_g <= 0) {  // local stage: one base pointer, constant stride between a thread's stores
         const SegDev &sg = Q.seg[0];
-        C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v + (long long)t * sg.os_d;
+        C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v + (long long)tB * sg.os_d;
         const long long step = (long long)TP * sg.os_d;
 #pragma unroll
         for (int m = 0; m < E; m++) out[m * step] = bwd ? cconj(v[m]) : v[m];
       } else {
 #pragma unroll
-        for (int m = 0; m < E; m++) store_out<T>(Q, t + m * TP, uo, vo, bwd ? cconj(v[m]) : v[m]);
+        for (int m = 0; m < E; m++) store_out<T>(Q, tB + m * TP, uo, vo, bwd ? cconj(v[m]) : v[m]);
       }
     }
   }
 }
 
-// ------------------------------------------------------------------ host side: lookup tables, one per (T, KIND, LM)
+// ------------------------------------------------------------------ host side: lookup tables, one per (T, KIND, TS)
 struct PipeInfo {
   void (*launch)(const StageParams &, int grid, cudaStream_t);
   const void *func;
-  int threads, xs, minb;
+  int threads, ts, minb;
   size_t smem;
 };
 
-template <typename T, int M, int KIND, int P, int LM> void pipe_launcher(const StageParams &Q, int grid, cudaStream_t s) {
-  typedef PipeCfg<T, M, KIND, P, LM> Cfg;
-  P3B_LAUNCH((pow2_pipe_kernel<T, M, KIND, P, LM>), grid, Cfg::THREADS, Cfg::smem, s, Q);
+template <typename T, int M, int KIND, int P, int TS> void pipe_launcher(const StageParams &Q, int grid, cudaStream_t s) {
+  typedef PipeCfg<T, M, KIND, P, TS> Cfg;
+  P3B_LAUNCH((pow2_pipe_kernel<T, M, KIND, P, TS>), grid, Cfg::THREADS, Cfg::smem, s, Q);
 }
 
-template <typename T, int M, int KIND, int P, int LM> const PipeInfo *pipe_info_one() {
-  typedef PipeCfg<T, M, KIND, P, LM> Cfg;
+template <typename T, int M, int KIND, int P, int TS> const PipeInfo *pipe_info_one() {
+  typedef PipeCfg<T, M, KIND, P, TS> Cfg;
   if constexpr (!Cfg::valid) {
     return nullptr;
   } else {
-    static const PipeInfo info = {pipe_launcher<T, M, KIND, P, LM>, (const void *)pow2_pipe_kernel<T, M, KIND, P, LM>, Cfg::THREADS,
-                                  Cfg::XS, Cfg::MINB, Cfg::smem};
+    static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, Cfg::THREADS,
+                                  TS, Cfg::MINB, Cfg::smem};
     return &info;
   }
 }
 
-template <typename T, int M, int KIND, int LM> const PipeInfo *pipe_info_m(int P) {
+template <typename T, int M, int KIND, int TS> const PipeInfo *pipe_info_m(int P) {
   switch (P) {
-    case 1: return pipe_info_one<T, M, KIND, 1, LM>();
-    case 2: return pipe_info_one<T, M, KIND, 2, LM>();
-    case 4: return pipe_info_one<T, M, KIND, 4, LM>();
-    case 8: return pipe_info_one<T, M, KIND, 8, LM>();
-    case 16: return pipe_info_one<T, M, KIND, 16, LM>();
+    case 1: return pipe_info_one<T, M, KIND, 1, TS>();
+    case 2: return pipe_info_one<T, M, KIND, 2, TS>();
+    case 4: return pipe_info_one<T, M, KIND, 4, TS>();
+    case 8: return pipe_info_one<T, M, KIND, 8, TS>();
+    case 16: return pipe_info_one<T, M, KIND, 16, TS>();
   }
   return nullptr;
 }
 
-template <typename T, int KIND, int LM> const PipeInfo *pipe_info(int M, int P) {
+template <typename T, int KIND, int TS> const PipeInfo *pipe_info(int M, int P) {
   switch (M) {
-    case 64: return pipe_info_m<T, 64, KIND, LM>(P);
-    case 128: return pipe_info_m<T, 128, KIND, LM>(P);
-    case 256: return pipe_info_m<T, 256, KIND, LM>(P);
-    case 512: return pipe_info_m<T, 512, KIND, LM>(P);
-    case 1024: return pipe_info_m<T, 1024, KIND, LM>(P);
-    case 2048: return pipe_info_m<T, 2048, KIND, LM>(P);
-    case 4096: return pipe_info_m<T, 4096, KIND, LM>(P);
+    case 64: return pipe_info_m<T, 64, KIND, TS>(P);
+    case 128: return pipe_info_m<T, 128, KIND, TS>(P);
+    case 256: return pipe_info_m<T, 256, KIND, TS>(P);
+    case 512: return pipe_info_m<T, 512, KIND, TS>(P);
+    case 1024: return pipe_info_m<T, 1024, KIND, TS>(P);
+    case 2048: return pipe_info_m<T, 2048, KIND, TS>(P);
+    case 4096: return pipe_info_m<T, 4096, KIND, TS>(P);
   }
   return nullptr;
 }
 
 // defined in pow2_pipe_inst.cu, compiled once per (precision, kind) so that the instantiations build in parallel
-const PipeInfo *pipe_lookup(int prec, int kind, int lm, int M, int P);
+const PipeInfo *pipe_lookup(int prec, int kind, int ts, int M, int P);
 
 }  // namespace p3b

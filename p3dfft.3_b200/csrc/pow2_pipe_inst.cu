@@ -13,12 +13,8 @@
 
 namespace p3b {
 
-const PipeInfo *PIPE_FN(int lm, int M, int P) {
-#if PIPE_KIND != 3  // real input (R2C) is only staged pencil-major
-  if (lm == LM_ROWS) return pipe_info<PIPE_T, PIPE_KIND, LM_ROWS>(M, P);
-#endif
-  if (lm != LM_PENCIL) return nullptr;
-  return pipe_info<PIPE_T, PIPE_KIND, LM_PENCIL>(M, P);
+const PipeInfo *PIPE_FN(int ts, int M, int P) {
+  return ts ? pipe_info<PIPE_T, PIPE_KIND, 1>(M, P) : pipe_info<PIPE_T, PIPE_KIND, 0>(M, P);
 }
 
 }  // namespace p3b

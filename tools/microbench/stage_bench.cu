@@ -136,43 +136,49 @@ int main(int argc, char **argv) {
     CK(cudaGetLastError());
     printf("%-38s %.3f ms  %.0f GB/s\n", name, ms, gb_c / ms * 1e3);
   };
-  if (N == 1024 && !(argc > 2)) {
+  auto run_pipe = [&](const PipeInfo *info, int ctas, const char *name) {
+    if (!info) { printf("%-38s (not instantiated)\n", name); return; }
+    CK(cudaFuncSetAttribute(info->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, info->func, info->threads, info->smem));
+    if (ctas <= 0 || ctas > occ) ctas = occ;
+    float ms = tm.run([&] { info->launch(P, sms * ctas, 0); });
+    CK(cudaGetLastError());
+    printf("%-38s %.3f ms  %.0f GB/s  (occ %d, used %d, smem %zu)\n", name, ms, gb_c / ms * 1e3, occ, ctas, info->smem);
+  };
+  if (N == 1024) {
     constexpr int M = 1024;
     size_t pen = (size_t)Pow2Smem<M>::PENCIL * 16;
-    set_tiles(8, 1, ORD_U, ORD_D);
-    run_old(pow2_stage_kernel<double, M, 512, 1>, 512, 8 * pen, 1, "Yfwd old P=8 512thr");
-    set_tiles(4, 1, ORD_U, ORD_D);
-    run_old(pow2_stage_kernel<double, M, 256, 2>, 256, 4 * pen, 2, "Yfwd old P=4 256thr x2");
-    set_tiles(8, 1, ORD_U, ORD_D);
-    run_old(pow2_pipe_kernel<double, M, 1, 8, LM_ROWS>, 512, PipeCfg<double, M, 1, 8, LM_ROWS>::smem, 1, "Yfwd pipe rows P=8");
-    // y-stage backward pattern: load D contiguous, store U runs: in {NY,NXC,NZ} mo 102 -> out mo 012
-    P.is_d = 1; P.is_u = NY; P.is_v = NY * NXC;
-    P.seg[0].os_d = NXC; P.seg[0].os_u = 1; P.seg[0].os_v = NXC * NY;
-    P.in = B; P.seg[0].base = A;
-    set_tiles(8, 1, ORD_D, ORD_U);
-    run_old(pow2_stage_kernel<double, M, 512, 1>, 512, 8 * pen, 1, "Ybwd old P=8 512thr");
-    set_tiles(4, 1, ORD_D, ORD_U);
-    run_old(pow2_stage_kernel<double, M, 256, 2>, 256, 4 * pen, 2, "Ybwd old P=4 256thr x2");
-    set_tiles(8, 1, ORD_D, ORD_U);
-    run_old(pow2_pipe_kernel<double, M, 1, 8, LM_PENCIL>, 512, PipeCfg<double, M, 1, 8, LM_PENCIL>::smem, 1, "Ybwd pipe pencil P=8");
-    // contiguous both sides (in-place layout, like a 1D batched FFT)
+    // (1) contiguous both sides: in {NY,NXC,NZ} pencils along y unit-stride, same layout out
     P.is_d = 1; P.is_u = NY; P.is_v = NY * NXC;
     P.seg[0].os_d = 1; P.seg[0].os_u = NY; P.seg[0].os_v = NY * NXC;
     P.in = A; P.seg[0].base = B;
-    set_tiles(8, 1, ORD_D, ORD_D);
-    run_old(pow2_stage_kernel<double, M, 512, 1>, 512, 8 * pen, 1, "contig old P=8 512thr");
     set_tiles(4, 1, ORD_D, ORD_D);
     run_old(pow2_stage_kernel<double, M, 256, 2>, 256, 4 * pen, 2, "contig old P=4 256thr x2");
-    set_tiles(2, 1, ORD_D, ORD_D);
-    run_old(pow2_stage_kernel<double, M, 128, 4>, 128, 2 * pen, 4, "contig old P=2 128thr x4");
-    set_tiles(1, 1, ORD_D, ORD_D);
-    run_old(pow2_stage_kernel<double, M, 64, 8>, 64, 1 * pen, 8, "contig old P=1 64thr x8");
-    set_tiles(4, 1, ORD_D, ORD_D);
-    run_old(pow2_pipe_kernel<double, M, 1, 4, LM_PENCIL>, 256, PipeCfg<double, M, 1, 4, LM_PENCIL>::smem, 1, "contig pipe P=4 x1");
-    set_tiles(2, 1, ORD_D, ORD_D);
-    run_old(pow2_pipe_kernel<double, M, 1, 2, LM_PENCIL>, 128, PipeCfg<double, M, 1, 2, LM_PENCIL>::smem, 3, "contig pipe P=2 x3");
-    set_tiles(1, 1, ORD_D, ORD_D);
-    run_old(pow2_pipe_kernel<double, M, 1, 1, LM_PENCIL>, 64, PipeCfg<double, M, 1, 1, LM_PENCIL>::smem, 6, "contig pipe P=1 x6");
+    for (int p : {1, 2, 4, 8}) {
+      char nm[64]; snprintf(nm, sizeof nm, "contig pipe P=%d", p);
+      set_tiles(p, 1, ORD_D, ORD_D);
+      run_pipe(pipe_info<double, 1, 0>(M, p), 0, nm);
+    }
+    // (2) contiguous loads, transposed stores along u: out {NXC(u) fastest, NY(d), NZ}
+    P.seg[0].os_d = NXC - 1; P.seg[0].os_u = 1; P.seg[0].os_v = (NXC - 1) * NY;  // u extent 512: aligned 128-byte runs
+    P.nu = NXC - 1;
+    for (int p : {2, 4, 8}) {
+      char nm[64]; snprintf(nm, sizeof nm, "transposed-u pipe P=%d", p);
+      set_tiles(p, 1, ORD_D, ORD_U);
+      run_pipe(pipe_info<double, 1, 1>(M, p), 0, nm);
+    }
+    set_tiles(8, 1, ORD_D, ORD_U);
+    run_old(pow2_stage_kernel<double, M, 512, 1>, 512, 8 * pen, 1, "transposed-u old P=8 512thr");
+    // (3) as the planner's y stage: in {NY(d) fastest, NXC(u), NZ(v)} -> out {NZ(v) fastest, NXC(u), NY(d)}
+    P.nu = NXC; P.nv = NZ;
+    P.seg[0].os_d = NZ * NXC; P.seg[0].os_u = NZ; P.seg[0].os_v = 1;
+    for (int p : {4, 8}) {
+      char nm[64]; snprintf(nm, sizeof nm, "transposed-v pipe P=%d", p);
+      set_tiles(1, p, ORD_D, ORD_V);
+      P.tiles_u = P.nu; P.ntiles = P.tiles_u * ((P.nv + p - 1) / p);
+      run_pipe(pipe_info<double, 1, 1>(M, p), 0, nm);
+    }
   }
   return 0;
 }
