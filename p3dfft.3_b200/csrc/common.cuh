@@ -49,6 +49,8 @@ struct StageParams {
   const void *in;
   long long nu, nv, is_d, is_u, is_v;
   long long tiles_u, ntiles;
+  long long tiles_v;  // pipelined kernel only: tile count along v and
+  int vfast;          // whether consecutive tile numbers run along v (else along u)
   int kind, dt_in, dt_out;
   int nfft, n_in, n_out, L;  // L = length of the internal complex FFT
   int tile_u, tile_v, tu_log2;

@@ -168,7 +168,8 @@ struct PipePlan {
   const p3b::PipeInfo *info = nullptr;
   int M = 0, P = 0, ld = 0, grid = 0;
   int tile_u = 1, tile_v = 1, tu_log2 = 0, load_ord = 0, store_ord = 0;
-  long long tiles_u = 0, ntiles = 0;
+  long long tiles_u = 0, tiles_v = 0, ntiles = 0;
+  int vfast = 0;
 };
 
 }  // namespace
@@ -335,7 +336,9 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   pp->load_ord = ORD_D;
   pp->store_ord = fout == 0 ? ORD_D : (fout == 1 ? ORD_U : ORD_V);
   pp->tiles_u = (d.nu + tu - 1) / tu;
-  pp->ntiles = pp->tiles_u * ((d.nv + tv - 1) / tv);
+  pp->tiles_v = (d.nv + tv - 1) / tv;
+  pp->ntiles = pp->tiles_u * pp->tiles_v;
+  pp->vfast = d.nv > 1 && (d.nu <= 1 || d.seg[0].os_v < d.seg[0].os_u);
   if (cudaFuncSetAttribute(info->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, info->func, info->threads, info->smem) != cudaSuccess) return 1;
@@ -343,8 +346,8 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   long long g = (long long)g_num_sms * occ;
   pp->grid = (int)(pp->ntiles < g ? (pp->ntiles > 0 ? pp->ntiles : 1) : g);
   char nm[220];
-  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s> threads=%d tile=%dx%d store=%d smem=%zu grid=%d occ=%d",
-           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", info->threads, tu, tv, pp->store_ord, info->smem,
+  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s> threads=%d tile=%dx%d%s store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", info->threads, tu, tv, pp->vfast ? " v-fast" : "", pp->store_ord, info->smem,
            pp->grid, occ);
   *name = nm;
   return 0;
@@ -509,7 +512,7 @@ int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int
     if (pp.ntiles > 0) {
       P.tile_u = pp.tile_u; P.tile_v = pp.tile_v; P.tu_log2 = pp.tu_log2;
       P.load_ord = pp.load_ord; P.store_ord = pp.store_ord;
-      P.tiles_u = pp.tiles_u; P.ntiles = pp.ntiles;
+      P.tiles_u = pp.tiles_u; P.tiles_v = pp.tiles_v; P.vfast = pp.vfast; P.ntiles = pp.ntiles;
       pp.info->launch(P, pp.grid, cs);
     }
   } else if (variant == V_POW2) {

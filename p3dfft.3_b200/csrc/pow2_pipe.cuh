@@ -163,6 +163,23 @@ __device__ __forceinline__ void reg_pass3(typename cx<T>::type *v, int t, const 
   }
 }
 
+// wt * exp(-2 pi i m / (2E)) for a compile-time m < E (E = 16: 32nd roots; E = 8: 16th roots)
+template <typename T, int E> __device__ __forceinline__ typename cx<T>::type real_twiddle(typename cx<T>::type wt, int m) {
+  // cos/sin(2 pi m / 32), m = 0..15
+  const double c32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                          0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0, -0.19509032201612826785,
+                          -0.38268343236508977173, -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                          -0.92387953251128675613, -0.98078528040323044913};
+  const double s32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474, 0.70710678118654752440,
+                          0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913, 1.0, 0.98078528040323044913,
+                          0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                          0.38268343236508977173, 0.19509032201612826785};
+  const int j = E == 16 ? m : 2 * m;
+  if (j == 0) return wt;
+  const T c = (T)c32[j], s = (T)s32[j];  // multiply by (c - i s)
+  return mk<T>(wt.x * c + wt.y * s, wt.y * c - wt.x * s);
+}
+
 // ------------------------------------------------------------------ the kernel
 template <typename T, int M, int KIND, int P, int TS>
 __global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, TS>::THREADS, PipeCfg<T, M, KIND, P, TS>::MINB)
@@ -204,9 +221,20 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   };
   // the pencil's leader thread starts the bulk copy of its pencil of tile `tl`; a pencil outside the array completes
   // the phase with zero bytes so that the waits stay uniform
+  // consecutive tile numbers (= concurrently running CTAs) run along the dimension that is closer to unit stride in the
+  // OUTPUT, so that the stores of neighbouring CTAs fill whole DRAM pages together
+  const bool vfast = Q.vfast != 0;
+  auto tile_origin = [&](long long tl, long long &u0, long long &v0) {
+    const long long iu = vfast ? tl / Q.tiles_v : tl % Q.tiles_u, iv = vfast ? tl % Q.tiles_v : tl / Q.tiles_u;
+    u0 = iu * tile_u;
+    v0 = iv * Q.tile_v;
+  };
   auto issue = [&](long long tl) {
     if (tA == 0 && tl < Q.ntiles) {
-      const long long u = (tl % Q.tiles_u) * tile_u + puA, v = (tl / Q.tiles_u) * Q.tile_v + pvA;
+      long long u, v;
+      tile_origin(tl, u, v);
+      u += puA;
+      v += pvA;
       const bool live = u < Q.nu && v < Q.nv;
       fence_async_smem();
       mbar_expect_tx(bar, live ? bytes : 0u);
@@ -218,6 +246,12 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
     }
   };
 
+  // real transforms: e^{-2 pi i k/N} for k = t + m TP factors into tw[t] (per thread, loop-invariant) and the
+  // compile-time 32nd root e^{-2 pi i m/32} (TP = M/16 = N/32)
+  C wt = mk<T>((T)1, (T)0);
+  if constexpr (r2c) wt = tw[tB];
+  if constexpr (c2r) wt = tw[tA];
+
   if (tid < P) mbar_init(bars + tid, 1);
   __syncthreads();
 
@@ -225,7 +259,10 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   unsigned parity = 0;
   issue(tile);
   for (; tile < Q.ntiles; tile += gridDim.x) {
-    const long long uo = (tile % Q.tiles_u) * tile_u + puB, vo = (tile / Q.tiles_u) * Q.tile_v + pvB;
+    long long uo, vo;
+    tile_origin(tile, uo, vo);
+    uo += puB;
+    vo += pvB;
     const bool live = uo < Q.nu && vo < Q.nv;
     C v[E];
     mbar_wait(bar, parity);  // this thread's pencil (mapping A) has landed
@@ -240,7 +277,7 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         C b = cconj(BA[M - k]);
         if (k == 0) { a.y = 0; b.y = 0; }  // FFTW's c2r ignores Im X[0] and Im X[N/2]
         C s = cadd(a, b), d = csub(a, b);
-        C w = cconj(__ldg(&tw[k]));
+        C w = cconj(real_twiddle<T, E>(wt, m));
         C e = cmuli(cmul(d, w));
         v[m] = cconj(cadd(s, e));
       }
@@ -287,16 +324,25 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         const C zk = v[m];
         const C zm = cconj(BB[padidx((M - k) & (M - 1))]);
         C s = cadd(zk, zm), d = csub(zk, zm);
-        C e = cmulmi(cmul(d, __ldg(&tw[k])));
+        C e = cmulmi(cmul(d, real_twiddle<T, E>(wt, m)));
         v[m] = mk<T>((T)0.5 * (s.x + e.x), (T)0.5 * (s.y + e.y));
         if (m == 0) xM = mk<T>(zk.x - zk.y, (T)0);  // X[M], used by the thread that owns k = 0
       }
       syncB();
       issue(tile + gridDim.x);
       if (live) {
+        if (Q.nseg == 1 && Q.deriv_g <= 0) {  // local stage: one base pointer, constant stride between a thread's stores
+          const SegDev &sg = Q.seg[0];
+          C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v + (long long)tB * sg.os_d;
+          const long long step = (long long)TP * sg.os_d;
 #pragma unroll
-        for (int m = 0; m < E; m++) store_out<T>(Q, tB + m * TP, uo, vo, v[m]);
-        if (tB == 0) store_out<T>(Q, M, uo, vo, xM);
+          for (int m = 0; m < E; m++) out[m * step] = v[m];
+          if (tB == 0) out[E * step] = xM;
+        } else {
+#pragma unroll
+          for (int m = 0; m < E; m++) store_out<T>(Q, tB + m * TP, uo, vo, v[m]);
+          if (tB == 0) store_out<T>(Q, M, uo, vo, xM);
+        }
       }
     } else if (c2r) {
       if (live) {  // conj(F(conj Z))[j] = x[2j] + i x[2j+1]; real output is never exchanged: one segment

@@ -97,7 +97,15 @@ double stage_cost(int d, const int mo_in[3], const int ld_in[3], const int mo_ou
   double c;
   if (fi == d && fo == d) c = 1.00;
   else if (fi == fo) c = 1.30;  // row-granular loads AND stores (measured slowest: 128-byte bulk copies per row)
-  else if (fi == d) c = 1.08;  // contiguous (TMA-prefetched) loads + transposed stores: stores do not stall the pipeline
+  else if (fi == d) {
+    c = 1.08;  // contiguous (TMA-prefetched) loads + transposed stores: stores do not stall the pipeline
+    // the stores of a tile are one short run per output index k: keep consecutive k close in memory (d second in the
+    // output order) so a tile touches a few pages instead of one 2 MB page per run (measured 5.9 vs 5.1 TB/s)
+    int before = 0;
+    for (int e = 0; e < 3; e++)
+      if (e != d && ld_out[e] > 1 && mo_out[e] < mo_out[d]) before++;
+    if (before >= 2) c += 0.05;
+  }
   else if (fo == d) c = 1.12;  // transposed loads + contiguous stores
   else c = 1.60;
   if (mo_in[0] == mo_out[0] && mo_in[1] == mo_out[1] && mo_in[2] == mo_out[2]) c -= 0.02;

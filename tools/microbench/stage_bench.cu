@@ -128,7 +128,8 @@ int main(int argc, char **argv) {
   P.seg[0].os_d = 1; P.seg[0].os_u = NY; P.seg[0].os_v = NY * NXC;
   auto set_tiles = [&](int tu, int tv, int lo, int so) {
     P.tile_u = tu; P.tile_v = tv; P.tu_log2 = ilog2(tu); P.load_ord = lo; P.store_ord = so;
-    P.tiles_u = (P.nu + tu - 1) / tu; P.ntiles = P.tiles_u * ((P.nv + tv - 1) / tv);
+    P.tiles_u = (P.nu + tu - 1) / tu; P.tiles_v = (P.nv + tv - 1) / tv; P.ntiles = P.tiles_u * P.tiles_v;
+    P.vfast = P.seg[0].os_v < P.seg[0].os_u;
   };
   auto run_old = [&](auto kern, int threads, size_t smem, int ctas, const char *name) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -176,7 +177,6 @@ int main(int argc, char **argv) {
     for (int p : {4, 8}) {
       char nm[64]; snprintf(nm, sizeof nm, "transposed-v pipe P=%d", p);
       set_tiles(1, p, ORD_D, ORD_V);
-      P.tiles_u = P.nu; P.ntiles = P.tiles_u * ((P.nv + p - 1) / p);
       run_pipe(pipe_info<double, 1, 1>(M, p), 0, nm);
     }
   }
