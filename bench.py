@@ -292,7 +292,8 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib.kernel_launches() - l0
-    # per-stage durations of the last step of the timed region (events recorded on the launch stream)
+    # per-stage durations averaged over the steps of the timed region (CUDA events recorded by the library on the launch
+    # stream around every stage kernel of every exec; read back only now, so nothing synchronises inside the region)
     stage_f += np.array(lib.stage_times(pf))
     stage_b += np.array(lib.stage_times(pb))
     clocks = sampler.stop() if rank == 0 else None
@@ -307,14 +308,47 @@ def main():
         for i, s in enumerate(d["stages"]):
             bytes_in = int(np.prod(s["in_ldims"])) * s["dt_in"] * d["prec"]
             bytes_out = int(np.prod(s["out_ldims"])) * s["dt_out"] * d["prec"]
-            stages.append({"stage": f"{name}{i}", "kind": s["kind"], "dim": s["dim"], "exchange": s["exchange"], "ms": float(t[i]),
-                           "alg_bytes": bytes_in + bytes_out, "gbs": (bytes_in + bytes_out) / (t[i] * 1e-3) / 1e9 if t[i] > 0 else None,
-                           "variant": s["variant"].split(" ")[0]})
-    dom = max(stages, key=lambda s: s["ms"])
+            st = {"stage": f"{name}{i}", "kind": s["kind"], "dim": s["dim"], "exchange": s["exchange"], "ms": float(t[i]),
+                  "alg_bytes": bytes_in + bytes_out, "gbs": (bytes_in + bytes_out) / (t[i] * 1e-3) / 1e9 if t[i] > 0 else None,
+                  "variant": s["variant"].split(" ")[0]}
+            if s["exchange"]:  # bytes this rank stores into OTHER GPUs' buffers over NVLink (local_bytes*(p-1)/p)
+                npen = s["in_ldims"][s["u"]] * s["in_ldims"][s["v"]]
+                st["nvlink_bytes"] = sum((g["k1"] - g["k0"]) * npen for g in s["segs"] if g["peer_world"] != rank) * s["dt_out"] * d["prec"]
+                st["nvlink_gbs"] = st["nvlink_bytes"] / (t[i] * 1e-3) / 1e9 if t[i] > 0 else None
+            stages.append(st)
+        # overlapped pairs (exchange stage + neighbouring local stage cut into chunks on two streams) are timed as a whole:
+        # the pair's duration is booked on both members, the local one carries no bandwidth figure of its own
+        base = len(stages) - len(d["stages"])
+        for i, s in enumerate(d["stages"]):
+            if s.get("pair"):
+                a, b = stages[base + i], stages[base + i + 1]
+                pair_ms = a["ms"] + b["ms"]
+                for m, o in ((a, b), (b, a)):
+                    m["ms"] = pair_ms
+                    m["overlapped_with"] = o["stage"]
+                    if m["exchange"]:
+                        m["nvlink_gbs"] = m["nvlink_bytes"] / (pair_ms * 1e-3) / 1e9
+                        m["gbs"] = None
+                    else:
+                        m["gbs"] = None
+    local = [s for s in stages if not s["exchange"] and s["gbs"]]
+    dom = max(local or stages, key=lambda s: s["ms"])  # dominant HBM-bound kernel (exchange stages: see "nvlink" below)
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak if dom["gbs"] else None,
                 "traffic": None, "kernel": f"{dom['variant']} ({dom['stage']}, dim {dom['dim']})", "peak_source": peak_src,
                 "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"], "stages": stages,
                 "whole_step_hbm_frac": sum(s["alg_bytes"] for s in stages) / (ms * 1e-3) / 1e9 / peak}
+    if not dom["gbs"]:
+        roofline["achieved"] = roofline["frac"] = None
+    xs = [s for s in stages if s["exchange"]]
+    if xs:  # fused FFT + all-to-all stages: NVLink roofline, 900 GB/s per direction per GPU (rank 0's figures)
+        xd = max(xs, key=lambda s: s["ms"])
+        tot_b, tot_ms = sum(s["nvlink_bytes"] for s in xs), sum(s["ms"] for s in xs)  # (pair durations include the hidden local stage)
+        roofline["nvlink"] = {"bound": "nvlink", "peak": 900.0, "unit": "GB/s", "peak_source": "NVLink 5 nominal, per direction per GPU",
+                              "achieved": xd["nvlink_gbs"], "frac": xd["nvlink_gbs"] / 900.0 if xd["nvlink_gbs"] else None,
+                              "kernel": f"{xd['variant']} ({xd['stage']}, dim {xd['dim']}, fused exchange)",
+                              "bytes_per_launch": xd["nvlink_bytes"], "ms_per_launch": xd["ms"],
+                              "all_exchanges": {"bytes": tot_b, "ms": tot_ms, "achieved": tot_b / (tot_ms * 1e-3) / 1e9, "frac": tot_b / (tot_ms * 1e-3) / 1e9 / 900.0},
+                              "whole_step_frac_of_exchange_bound": (tot_b / 900e9) / (ms * 1e-3)}
     traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:

@@ -36,7 +36,8 @@ long long p3dfft_b200_kernel_launches(void);
 /* JSON description of a 3D plan (stages, layouts, exchange segments); returns bytes needed */
 size_t p3dfft_b200_describe_plan3d(int plan, char *buf, size_t buflen);
 size_t p3dfft_b200_describe_plan1d(int plan, char *buf, size_t buflen);
-/* per-stage CUDA-event timing: 1 = on.  Read back with p3dfft_b200_stage_times (ms of the last exec) */
+/* per-stage CUDA-event timing: 1 = on.  Read back with p3dfft_b200_stage_times (ms per stage,
+   averaged over the execs of that plan since the previous read, at most 64) */
 void p3dfft_b200_enable_timers(int on);
 int p3dfft_b200_stage_times(int plan, float *ms, int max_stages);
 /* 1 if a usable CUDA device was found at p3dfft_setup() (plans can be built and inspected without one) */
@@ -104,6 +105,9 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out);
 int p3dfftcu_stage_destroy(p3dfftcu_stage st);
 /* deriv_g > 0: multiply output k by i*k (k<g/2), 0 (k==g/2), i*(k-g) (k>g/2)  (exec.C:228-287) */
 int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream);
+/* same, with the number of CTAs capped at max_ctas (<= 0: no cap): lets two stages share the SMs when they overlap */
+int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
+                               int max_ctas);
 /* human-readable name of the kernel variant picked for this stage */
 const char *p3dfftcu_stage_variant(p3dfftcu_stage st);
 
@@ -111,7 +115,13 @@ const char *p3dfftcu_stage_variant(p3dfftcu_stage st);
  * kappa from global index gstart+local index and full length g (deriv.C:85-185) */
 int p3dfftcu_deriv(const void *in, void *out, int prec, const int sd[3], int ldir, int g, int gstart, void *stream);
 
-/* events (per-stage timers) */
+/* side stream for overlapped stages: high_priority != 0 asks for the device's greatest priority */
+int p3dfftcu_stream_create(void **stream, int high_priority);
+int p3dfftcu_stream_destroy(void *stream);
+int p3dfftcu_stream_wait_event(void *stream, void *ev);
+int p3dfftcu_num_sms(void);
+
+/* events (per-stage timers, cross-stream dependencies) */
 int p3dfftcu_event_create(void **ev);
 int p3dfftcu_event_destroy(void *ev);
 int p3dfftcu_event_record(void *ev, void *stream);

@@ -65,7 +65,8 @@ EXT_SYMBOLS = [
 CU_SYMBOLS = [
     "p3dfftcu_last_error", "p3dfftcu_device_count", "p3dfftcu_init", "p3dfftcu_malloc", "p3dfftcu_free",
     "p3dfftcu_memset", "p3dfftcu_memcpy", "p3dfftcu_stream_sync", "p3dfftcu_pointer_is_device",
-    "p3dfftcu_stage_create", "p3dfftcu_stage_destroy", "p3dfftcu_stage_exec", "p3dfftcu_stage_variant",
+    "p3dfftcu_stage_create", "p3dfftcu_stage_destroy", "p3dfftcu_stage_exec", "p3dfftcu_stage_exec_capped", "p3dfftcu_stage_variant",
+    "p3dfftcu_stream_create", "p3dfftcu_stream_destroy", "p3dfftcu_stream_wait_event", "p3dfftcu_num_sms",
     "p3dfftcu_deriv", "p3dfftcu_event_create", "p3dfftcu_event_destroy", "p3dfftcu_event_record",
     "p3dfftcu_event_elapsed", "p3dfftcu_ipc_export", "p3dfftcu_ipc_open", "p3dfftcu_ipc_close",
     "p3dfftcu_peer_barrier", "p3dfftcu_launch_count",

@@ -491,6 +491,11 @@ int p3dfftcu_stage_destroy(p3dfftcu_stage st) {
 const char *p3dfftcu_stage_variant(p3dfftcu_stage st) { return st->name.c_str(); }
 
 int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream) {
+  return p3dfftcu_stage_exec_capped(st, in, dst, ndst, deriv_g, stream, 0);
+}
+
+int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
+                               int max_ctas) {
   if (deriv_g > 0 && st->d.dt_out != 2) return failmsg("stage: spectral derivative needs complex output");
   StageParams P = st->P;
   P.in = in;
@@ -513,15 +518,23 @@ int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int
       P.tile_u = pp.tile_u; P.tile_v = pp.tile_v; P.tu_log2 = pp.tu_log2;
       P.load_ord = pp.load_ord; P.store_ord = pp.store_ord;
       P.tiles_u = pp.tiles_u; P.tiles_v = pp.tiles_v; P.vfast = pp.vfast; P.ntiles = pp.ntiles;
-      pp.info->launch(P, pp.grid, cs);
+      int grid = pp.grid;
+      if (st->d.nseg > 1) {  // tuning: cap the CTAs of a fused exchange stage (NVLink-bound: may not need every SM)
+        static const int xcap = getenv("P3DFFT_B200_XGRID") ? atoi(getenv("P3DFFT_B200_XGRID")) : 0;
+        if (xcap > 0 && grid > xcap) grid = xcap;
+      }
+      if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+      pp.info->launch(P, grid, cs);
     }
   } else if (variant == V_POW2) {
-    int rc = pow2_launch(st->pw, P, cs);
+    Pow2Plan pw = st->pw;
+    if (max_ctas > 0 && pw.grid > max_ctas) pw.grid = max_ctas;
+    int rc = pow2_launch(pw, P, cs);
     if (rc) return failmsg(std::string("pow2 stage launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-  } else if (st->d.prec == 8) {
-    P3B_LAUNCH(generic_stage_kernel<double>, st->grid, st->threads, st->smem, cs, P);
   } else {
-    P3B_LAUNCH(generic_stage_kernel<float>, st->grid, st->threads, st->smem, cs, P);
+    const int grid = (max_ctas > 0 && st->grid > max_ctas) ? max_ctas : st->grid;
+    if (st->d.prec == 8) P3B_LAUNCH(generic_stage_kernel<double>, grid, st->threads, st->smem, cs, P);
+    else P3B_LAUNCH(generic_stage_kernel<float>, grid, st->threads, st->smem, cs, P);
   }
   g_launches++;
   CK(cudaGetLastError());
@@ -542,6 +555,24 @@ int p3dfftcu_deriv(const void *in, void *out, int prec, const int sd[3], int ldi
   CK(cudaGetLastError());
   return 0;
 }
+
+int p3dfftcu_stream_create(void **stream, int high_priority) {
+  int lo = 0, hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // numerically lower = greater priority
+  cudaStream_t s;
+  CK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+  *stream = s;
+  return 0;
+}
+int p3dfftcu_stream_destroy(void *stream) {
+  if (stream) CK(cudaStreamDestroy((cudaStream_t)stream));
+  return 0;
+}
+int p3dfftcu_stream_wait_event(void *stream, void *ev) {
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+  return 0;
+}
+int p3dfftcu_num_sms(void) { return g_num_sms; }
 
 int p3dfftcu_event_create(void **ev) {
   cudaEvent_t e;

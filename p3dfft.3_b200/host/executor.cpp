@@ -137,6 +137,78 @@ static void peer_barrier(Plan *pl, const StagePlan &st, void *stream) {
   GPU(p3dfftcu_peer_barrier(pf, slots, n, ws.flags, pl->rank, ws.epoch, stream), pl, "peer barrier");
 }
 
+// CTA budgets of an overlapped pair: the exchange stage is NVLink-bound and keeps its speed on about half of the SMs
+// (measured on 2 GPUs: 148 -> 74 CTAs costs 3 %), the local stage gets the rest
+static void pair_caps(int *xcap, int *lcap) {
+  static int sms = p3dfftcu_num_sms();
+  static int xs = [] {
+    const char *e = getenv("P3DFFT_B200_OVERLAP_XSMS");
+    int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 0;
+  }();
+  int x = xs > 0 ? xs : sms / 2;
+  if (x >= sms) x = sms - 1;
+  if (x < 1) x = 1;
+  *xcap = x;              // one CTA per SM (the exchange kernels fill an SM's registers)
+  *lcap = 2 * (sms - x);  // the local kernels run two CTAs per SM
+}
+
+// runs stages s (first) and s+1 of an overlapped pair; `ssrc` = input of stage s, `ldst` = output of the local stage
+static void run_pair(Plan *pl, size_t s, const void *ssrc, void *ldst, const int deriv_g[2], void *stream) {
+  Workspace &ws = g_ws;
+  StagePlan &first = pl->stages[s], &second = pl->stages[s + 1];
+  const bool l_first = first.pair == StagePlan::PAIR_L_THEN_X;
+  StagePlan &L = l_first ? first : second, &X = l_first ? second : first;
+  const size_t xs = l_first ? s + 1 : s;  // index of the exchange stage: it writes the peers' buffers w
+  const int w = (int)(xs & 1);
+  const int gL = deriv_g[l_first ? 0 : 1], gX = deriv_g[l_first ? 1 : 0];
+  void *xdsts[P3DFFTCU_MAXSEG];
+  for (size_t q = 0; q < X.peers.size(); q++) xdsts[q] = ws.peer_buf[w][X.peers[q].peer_world];
+  void *xstream = pl->xstream;
+  std::vector<void *> &ev = pl->sync_events;  // [0] fork, [1] join, [2 + c] chunk c of the first stage is complete
+  const size_t C = X.chunks.size();
+  int xcap, lcap;
+  pair_caps(&xcap, &lcap);
+  GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
+  GPU(p3dfftcu_stream_wait_event(xstream, ev[0]), pl, "stream wait");
+  peer_barrier(pl, X, xstream);  // every peer has finished reading its buffer w
+  if (l_first) {
+    // main stream: L chunk by chunk into my work buffer; side stream: X on each chunk as soon as it is complete
+    void *lbuf = ws.buf[s & 1];
+    for (size_t c = 0; c < C; c++) {
+      if (L.chunks[c].handle) {
+        void *d1[1] = {lbuf};
+        GPU(p3dfftcu_stage_exec_capped(L.chunks[c].handle, (const char *)ssrc + L.chunks[c].in_off_bytes, d1, 1, gL, stream,
+                                       c == 0 ? 0 : lcap), pl, "stage launch");
+      }
+      GPU(p3dfftcu_event_record(ev[2 + c], stream), pl, "event");
+      GPU(p3dfftcu_stream_wait_event(xstream, ev[2 + c]), pl, "stream wait");
+      if (X.chunks[c].handle)
+        GPU(p3dfftcu_stage_exec_capped(X.chunks[c].handle, (const char *)lbuf + X.chunks[c].in_off_bytes, xdsts, (int)X.peers.size(),
+                                       gX, xstream, c + 1 == C ? 0 : xcap), pl, "stage launch");
+    }
+    peer_barrier(pl, X, xstream);  // every peer's blocks have landed in my buffer w
+  } else {
+    // side stream: X chunk by chunk, each followed by a barrier (chunk c of every peer has landed); main stream: L on
+    // each chunk of the received array
+    for (size_t c = 0; c < C; c++) {
+      if (X.chunks[c].handle)
+        GPU(p3dfftcu_stage_exec_capped(X.chunks[c].handle, (const char *)ssrc + X.chunks[c].in_off_bytes, xdsts, (int)X.peers.size(),
+                                       gX, xstream, c == 0 ? 0 : xcap), pl, "stage launch");
+      peer_barrier(pl, X, xstream);
+      GPU(p3dfftcu_event_record(ev[2 + c], xstream), pl, "event");
+      GPU(p3dfftcu_stream_wait_event(stream, ev[2 + c]), pl, "stream wait");
+      if (L.chunks[c].handle) {
+        void *d1[1] = {ldst};
+        GPU(p3dfftcu_stage_exec_capped(L.chunks[c].handle, (const char *)ws.buf[w] + L.chunks[c].in_off_bytes, d1, 1, gL, stream,
+                                       c + 1 == C ? 0 : lcap), pl, "stage launch");
+      }
+    }
+  }
+  GPU(p3dfftcu_event_record(ev[1], xstream), pl, "event");
+  GPU(p3dfftcu_stream_wait_event(stream, ev[1]), pl, "stream wait");
+}
+
 static void add_timer(const StagePlan &st, bool deriv, double sec) {
   if (st.kind == P3DFFTCU_K_EMPTY) {
     if (st.exchange) timers.alltoall += sec;
@@ -190,27 +262,52 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
   const size_t S = pl->stages.size();
   const bool timing = timers_on();
   std::vector<void *> &ev = pl->events;
+  size_t ev0 = 0;  // first event of this exec: every exec since the last read keeps its own S+1 events (up to 64 execs)
   if (timing) {
-    while (ev.size() < S + 1) {
+    if (pl->timed_execs >= 64) pl->timed_execs = 0;
+    ev0 = (size_t)pl->timed_execs * (S + 1);
+    while (ev.size() < ev0 + S + 1) {
       void *e = nullptr;
       GPU(p3dfftcu_event_create(&e), pl, "event");
       ev.push_back(e);
     }
-    GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
+    GPU(p3dfftcu_event_record(ev[ev0], stream), pl, "event");
   }
   int deriv_stage = -1;
-  for (size_t s = 0; s < S; s++) {
-    StagePlan &st = pl->stages[s];
-    const void *ssrc = s == 0 ? src : ws.buf[(s - 1) & 1];
-    const bool last = s + 1 == S;
-    int deriv_g = 0;
+  auto deriv_len = [&](size_t s) {
+    const StagePlan &st = pl->stages[s];
     if (idir >= 0 && st.dim == idir && st.kind != P3DFFTCU_K_EMPTY) {
       if (st.dt_out != 2) printf("Error in exec_deriv: expected complex output type\n");
       else {
-        deriv_g = st.kind == P3DFFTCU_K_R2C ? (st.n_out - 1) * 2 : st.n_out;  // exec.C:240-246
         deriv_stage = (int)s;
+        return st.kind == P3DFFTCU_K_R2C ? (st.n_out - 1) * 2 : st.n_out;  // exec.C:240-246
       }
     }
+    return 0;
+  };
+  for (size_t s = 0; s < S; s++) {
+    StagePlan &st = pl->stages[s];
+    const void *ssrc = s == 0 ? src : ws.buf[(s - 1) & 1];
+    if (st.pair != StagePlan::PAIR_NONE && s + 1 < S) {
+      // overlapped pair: the local stage's output is my work buffer, or the user's array when it is the last stage
+      const bool l_first = st.pair == StagePlan::PAIR_L_THEN_X;
+      const size_t ls = l_first ? s : s + 1;
+      void *ldst = ls + 1 == S ? dst : ws.buf[ls & 1];
+      if (l_first || (const void *)ldst != ssrc) {  // (in-place call whose output would overwrite X's input: run in sequence)
+        const int dg[2] = {deriv_len(s), deriv_len(s + 1)};
+        run_pair(pl, s, ssrc, ldst, dg, stream);
+        if (l_first && s + 2 == S)  // the exchange stage is the plan's last: its result sits in my work buffer
+          GPU(p3dfftcu_memcpy(dst, ws.buf[(s + 1) & 1], (size_t)pl->stages[s + 1].out_bytes, 2, stream), pl, "device copy");
+        if (timing) {  // the pair is timed as a whole: its duration is booked on the first stage, zero on the second
+          GPU(p3dfftcu_event_record(ev[ev0 + s + 1], stream), pl, "event");
+          GPU(p3dfftcu_event_record(ev[ev0 + s + 2], stream), pl, "event");
+        }
+        s++;
+        continue;
+      }
+    }
+    const bool last = s + 1 == S;
+    const int deriv_g = deriv_len(s);
     if (st.exchange) {
       const int w = (int)(s & 1);
       void *dsts[P3DFFTCU_MAXSEG];
@@ -227,7 +324,7 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
       GPU(p3dfftcu_stage_exec(st.handle, ssrc, dsts, 1, deriv_g, stream), pl, "stage launch");
       if (bounce) GPU(p3dfftcu_memcpy(dst, sdst, (size_t)st.out_bytes, 2, stream), pl, "device copy");
     }
-    if (timing) GPU(p3dfftcu_event_record(ev[s + 1], stream), pl, "event");
+    if (timing) GPU(p3dfftcu_event_record(ev[ev0 + s + 1], stream), pl, "event");
   }
   if (!out_dev) {
     GPU(p3dfftcu_memcpy(out, dst, (size_t)pl->out_bytes, 1, stream), pl, "device->host copy");
@@ -235,21 +332,28 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
   } else if (!in_dev) {
     GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");  // the host input may be reused by the caller
   }
+  if (timing) pl->timed_execs++;
   pl->events_valid = timing;
   pl->last_deriv_stage = deriv_stage;
 }
 
-// per-stage milliseconds of the most recent exec (waits for it to finish); also feeds p3dfft::timers
+// per-stage milliseconds averaged over the execs since the last read (waits for them to finish); also feeds p3dfft::timers
 void plan_collect_times(Plan *pl) {
-  if (!pl->events_valid) return;
+  if (!pl->events_valid || pl->timed_execs < 1) return;
   const size_t S = pl->stages.size();
   for (size_t s = 0; s < S; s++) {
-    float ms = 0;
-    GPU(p3dfftcu_event_elapsed(pl->events[s], pl->events[s + 1], &ms), pl, "event");
-    pl->stage_ms[s] = ms;
-    add_timer(pl->stages[s], (int)s == pl->last_deriv_stage, ms * 1e-3);
+    double sum = 0;
+    for (int x = 0; x < pl->timed_execs; x++) {
+      float ms = 0;
+      const size_t e = (size_t)x * (S + 1) + s;
+      GPU(p3dfftcu_event_elapsed(pl->events[e], pl->events[e + 1], &ms), pl, "event");
+      sum += ms;
+    }
+    pl->stage_ms[s] = (float)(sum / pl->timed_execs);
+    add_timer(pl->stages[s], (int)s == pl->last_deriv_stage, sum * 1e-3);
   }
   pl->events_valid = false;
+  pl->timed_execs = 0;
 }
 
 }  // namespace b200

@@ -45,7 +45,18 @@ struct StagePlan {
   p3dfftcu_stage handle;
   long long out_bytes;  // bytes of this rank's output block
   long long in_bytes;
-  StagePlan() : handle(nullptr) {}
+  // overlap of a fused exchange stage X with a neighbouring local stage L (north_star: "overlapped with the FFT of the
+  // next pencil batch"): both stages are cut into the same chunks along a dimension neither of them transforms and run on
+  // two streams, chunk c of the later stage waiting for chunk c of the earlier one
+  enum { PAIR_NONE = 0, PAIR_L_THEN_X = 1, PAIR_X_THEN_L = 2 };
+  int pair;             // set on the FIRST stage of a pair (the second one is the next stage); PAIR_NONE otherwise
+  int chunk_dim;        // logical dimension the pair is cut along
+  struct Chunk {
+    p3dfftcu_stage handle;   // nullptr: empty on this rank (the barrier of the chunk still runs)
+    long long in_off_bytes;  // byte offset of the chunk in the stage's input array
+  };
+  std::vector<Chunk> chunks;  // on BOTH stages of a pair, same count on every rank
+  StagePlan() : handle(nullptr), pair(PAIR_NONE), chunk_dim(-1) {}
 };
 
 struct Plan {
@@ -61,12 +72,16 @@ struct Plan {
   long long in_bytes, out_bytes;  // user-visible array sizes on this rank
   long long work_bytes;           // per work buffer, max over stages and ranks
   std::vector<float> stage_ms;
-  std::vector<void *> events;  // S+1 CUDA events recorded around the stages when timers are on
+  std::vector<void *> events;  // (S+1) CUDA events per exec recorded around the stages while timers are on
+  int timed_execs;             // execs recorded since the stage times were last read (events [0, timed_execs*(S+1)))
   bool events_valid;
   int last_deriv_stage;
   // device staging for host-pointer calls
   void *dev_in, *dev_out;
   long long dev_in_bytes, dev_out_bytes;
+  // overlapped pairs: high-priority side stream for the exchange stage, fork/join and per-chunk events
+  void *xstream;
+  std::vector<void *> sync_events;
   Plan();
   ~Plan();
 };

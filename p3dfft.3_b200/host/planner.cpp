@@ -340,6 +340,106 @@ void fill_stage(StagePlan &st, const ProtoStage &p, const int mo_in[3], const in
   }
 }
 
+// ---- overlap pairs: cut an exchange stage X and a neighbouring local stage L into the same chunks
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// chunk [c0, c1) of stage st along logical dimension cdim (one of st.u, st.v)
+bool make_chunk(const StagePlan &st, int prec, int cdim, int c0, int c1, StagePlan::Chunk *out, std::string *err) {
+  out->handle = nullptr;
+  out->in_off_bytes = 0;
+  if (c1 <= c0) return true;
+  p3dfftcu_stage_desc d = st.desc;
+  const bool along_u = cdim == st.u;
+  long long in_off;
+  if (along_u) {
+    d.nu = c1 - c0;
+    in_off = (long long)c0 * d.is_u;
+    for (int q = 0; q < d.nseg; q++) d.seg[q].off += (long long)c0 * d.seg[q].os_u;
+  } else {
+    d.nv = c1 - c0;
+    in_off = (long long)c0 * d.is_v;
+    for (int q = 0; q < d.nseg; q++) d.seg[q].off += (long long)c0 * d.seg[q].os_v;
+  }
+  out->in_off_bytes = in_off * st.dt_in * prec;
+  if (p3dfftcu_stage_create(&d, &out->handle)) {
+    *err = std::string("chunk stage setup failed: ") + p3dfftcu_last_error();
+    return false;
+  }
+  return true;
+}
+
+bool plan_overlap(Plan *pl, const std::vector<ProtoStage> &protos) {
+  const size_t S = pl->stages.size();
+  if (pl->nranks < 2 || S < 2 || !env_int("P3DFFT_B200_OVERLAP", 1)) return true;
+  int nchunks = env_int("P3DFFT_B200_OVERLAP_CHUNKS", 4);
+  if (nchunks < 2) return true;
+  if (nchunks > 16) nchunks = 16;
+  std::vector<bool> used(S, false);
+  for (size_t x = 0; x < S; x++) {
+    StagePlan &X = pl->stages[x];
+    if (!X.exchange || X.kind == P3DFFTCU_K_EMPTY || used[x]) continue;
+    // candidate partners: the local stage before (its input must not be the buffer the peers write: it has to be the
+    // user's array, i.e. stage 0) or after (its output must not be the buffer X reads: last stage, or X is stage 0)
+    int l = -1, mode = StagePlan::PAIR_NONE;
+    if (x >= 1 && x - 1 == 0 && !used[x - 1] && !pl->stages[x - 1].exchange && pl->stages[x - 1].kind != P3DFFTCU_K_EMPTY) {
+      l = (int)x - 1;
+      mode = StagePlan::PAIR_L_THEN_X;
+    } else if (x + 1 < S && !used[x + 1] && !pl->stages[x + 1].exchange && pl->stages[x + 1].kind != P3DFFTCU_K_EMPTY &&
+               (x + 2 == S || x == 0)) {
+      l = (int)x + 1;
+      mode = StagePlan::PAIR_X_THEN_L;
+    }
+    if (l < 0) continue;
+    StagePlan &L = pl->stages[l];
+    if (L.dim == X.dim) continue;
+    const int cdim = 3 - L.dim - X.dim;
+    // X before L: the chunks are ranges of the RECEIVED array, so cdim must keep its distribution across the exchange
+    if (mode == StagePlan::PAIR_X_THEN_L && cdim == X.xdim_gather) continue;
+    // rank-independent chunk size from the largest block of cdim (every rank must run the same number of barriers);
+    // multiples of 16 keep the tiles of both stages whole
+    const ProtoStage &px = protos[x];
+    const int rep = mode == StagePlan::PAIR_L_THEN_X ? px.rep_in[cdim] : px.rep_out[cdim];
+    int cs = (rep + nchunks - 1) / nchunks;
+    int align = env_int("P3DFFT_B200_OVERLAP_ALIGN", 16);  // (tests use 1 to cut small and uneven grids)
+    if (align < 1) align = 1;
+    cs = (cs + align - 1) / align * align;
+    if (cs <= 0 || rep < 2 * cs) continue;  // too small to be worth cutting
+    const int C = (rep + cs - 1) / cs;
+    const int mine = mode == StagePlan::PAIR_L_THEN_X ? X.in.ldims[cdim] : X.out.ldims[cdim];
+    StagePlan &first = mode == StagePlan::PAIR_L_THEN_X ? L : X;
+    first.pair = mode;
+    L.chunk_dim = X.chunk_dim = cdim;
+    L.chunks.resize(C);
+    X.chunks.resize(C);
+    for (int c = 0; c < C; c++) {
+      const int c0 = std::min(c * cs, mine), c1 = std::min((c + 1) * cs, mine);
+      if (!make_chunk(L, pl->prec, cdim, c0, c1, &L.chunks[c], &pl->error)) return false;
+      if (!make_chunk(X, pl->prec, cdim, c0, c1, &X.chunks[c], &pl->error)) return false;
+    }
+    used[x] = used[l] = true;
+  }
+  bool any = false;
+  for (size_t s = 0; s < S; s++) any = any || pl->stages[s].pair != StagePlan::PAIR_NONE;
+  if (any) {
+    if (p3dfftcu_stream_create(&pl->xstream, 1)) {
+      pl->error = std::string("side stream: ") + p3dfftcu_last_error();
+      return false;
+    }
+    for (int i = 0; i < 2 + 16; i++) {
+      void *e = nullptr;
+      if (p3dfftcu_event_create(&e)) {
+        pl->error = std::string("event: ") + p3dfftcu_last_error();
+        return false;
+      }
+      pl->sync_events.push_back(e);
+    }
+  }
+  return true;
+}
+
 bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vector<int> &perm) {
   const int *mo1 = pl->g1->MemOrder, *mo2 = pl->g2->MemOrder;
   size_t S = protos.size();
@@ -369,6 +469,7 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
         return false;
       }
     }
+    if (!plan_overlap(pl, protos)) return false;
     bool need_ws = S > 1 || pl->nranks > 1;
     for (size_t s = 0; s < S; s++) need_ws = need_ws || pl->stages[s].exchange;
     std::string err;
@@ -384,12 +485,17 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
 
 Plan::Plan()
     : ok(false), prec(0), dt_in(0), dt_out(0), nranks(1), rank(0), comm(MPI_COMM_NULL), g1(nullptr), g2(nullptr), pgrid(nullptr),
-      in_bytes(0), out_bytes(0), work_bytes(0), events_valid(false), last_deriv_stage(-1), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0) {}
+      in_bytes(0), out_bytes(0), work_bytes(0), timed_execs(0), events_valid(false), last_deriv_stage(-1), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0), xstream(nullptr) {}
 
 Plan::~Plan() {
-  for (size_t s = 0; s < stages.size(); s++)
+  for (size_t s = 0; s < stages.size(); s++) {
     if (stages[s].handle) p3dfftcu_stage_destroy(stages[s].handle);
+    for (size_t c = 0; c < stages[s].chunks.size(); c++)
+      if (stages[s].chunks[c].handle) p3dfftcu_stage_destroy(stages[s].chunks[c].handle);
+  }
   for (size_t i = 0; i < events.size(); i++) p3dfftcu_event_destroy(events[i]);
+  for (size_t i = 0; i < sync_events.size(); i++) p3dfftcu_event_destroy(sync_events[i]);
+  if (xstream) p3dfftcu_stream_destroy(xstream);
   if (dev_in) p3dfftcu_free(dev_in);
   if (dev_out) p3dfftcu_free(dev_out);
   delete g1;
@@ -590,6 +696,7 @@ std::string describe(const Plan &p) {
     put3(o, "out_ldims", st.out.ldims);
     o << ",";
     put3(o, "out_mo", st.out.mo);
+    o << ",\"pair\":" << st.pair << ",\"chunk_dim\":" << st.chunk_dim << ",\"chunks\":" << st.chunks.size();
     o << ",\"variant\":\"" << (st.handle ? p3dfftcu_stage_variant(st.handle) : "") << "\",\"segs\":[";
     for (int q = 0; q < st.desc.nseg; q++) {
       const p3dfftcu_seg &g = st.desc.seg[q];

@@ -51,6 +51,8 @@ def main():
         plan = lib.plan_3Dtrans(g1, g2, lib.init_3Dtype(types))
         desc = lib.describe_plan3d(plan)
         assert desc["ok"], desc
+        if os.environ.get("P3DFFT_TEST_EXPECT_PAIRS") and c.get("expect_pairs", True):
+            assert any(s["pair"] for s in desc["stages"]), ("no overlapped pair planned", desc)
         og1 = orc.OGrid(g1d, c["dmap1"], c["mo1"], pd, rank, c.get("cs1", -1))
         og2 = orc.OGrid(g2d, c["dmap2"], c["mo2"], pd, rank, c.get("cs2", -1))
         assert list(g1.contents.Ldims) == og1.Ldims and list(g1.contents.GlobStart) == og1.GlobStart

@@ -37,7 +37,7 @@ def c2c(n, pd, **kw):
     return c
 
 
-def launch(nranks, cases, mode="emu", gloo=False, timeout=900):
+def launch(nranks, cases, mode="emu", gloo=False, timeout=900, env_extra=None):
     arg = cases if isinstance(cases, str) else json.dumps(cases)
     if gloo:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
@@ -47,6 +47,7 @@ def launch(nranks, cases, mode="emu", gloo=False, timeout=900):
                os.path.join(HERE, "mp_worker.py"), mode, arg]
     env = dict(os.environ)
     env.pop("P3DFFT_B200_PLAN_ONLY", None)
+    env.update(env_extra or {})
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     ok = out.returncode == 0 and out.stdout.count(" OK worst") == nranks
     assert ok, (out.stdout[-3000:], out.stderr[-3000:])
@@ -118,6 +119,22 @@ def test_other_distributions_and_empty_types():
              cs2=0, **XP),                                                 # sample/C/test2D+empty.c
     ]
     launch(4, cs)
+
+
+FORCE_PAIRS = {"P3DFFT_B200_OVERLAP_ALIGN": "1", "P3DFFT_B200_OVERLAP_CHUNKS": "3", "P3DFFT_TEST_EXPECT_PAIRS": "1"}
+
+
+def test_overlapped_exchange_pairs():
+    """an exchange stage and its neighbouring local stage cut into chunks on two streams (per-chunk peer barriers):
+    slab forward (local stage first) and backward (exchange first), pencil grids, uneven blocks with empty chunks,
+    fused derivative; small grids are cut by lifting the chunk alignment"""
+    n = (16, 12, 10)
+    launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2]), c2c(n, [1, 1, 2]), fwd(n, [1, 1, 2], deriv=1), fwd(n, [1, 1, 2], deriv=0)],
+           env_extra=FORCE_PAIRS)
+    launch(3, [fwd((14, 7, 11), [1, 1, 3]), bwd((14, 7, 11), [1, 1, 3])], env_extra=FORCE_PAIRS)
+    launch(4, [fwd((32, 24, 20), [1, 2, 2]), bwd((32, 24, 20), [1, 2, 2]), fwd(n, [1, 2, 2], deriv=2), c2c(n, [1, 4, 1])],
+           env_extra=FORCE_PAIRS)
+    launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2])], env_extra={"P3DFFT_B200_OVERLAP": "0"})
 
 
 # ------------------------------------------------------------------------------------------------ real GPUs

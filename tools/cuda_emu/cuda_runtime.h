@@ -94,6 +94,11 @@ inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { mem
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum { cudaStreamNonBlocking = 1 };
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = malloc(8); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // launches run in issue order
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = malloc(8); return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
