@@ -84,6 +84,9 @@ typedef struct p3dfftcu_stage_desc {
   long long nu, nv;
   long long is_d, is_u, is_v;
   p3dfftcu_seg seg[P3DFFTCU_MAXSEG];
+  int whole_sm_ctas; /* != 0: prefer a kernel shape whose CTA fills an SM (one CTA per SM), so that the CTA cap of
+                        p3dfftcu_stage_exec_capped partitions the SMs cleanly between two overlapped stages */
+  int pad2_;
 } p3dfftcu_stage_desc;
 
 typedef struct p3dfftcu_stage_s *p3dfftcu_stage;

@@ -299,6 +299,10 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   const int E = M == 64 ? 8 : 16, TP = M / E;
   // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
   int want = ts ? (int)(128 / csz) : (256 / TP > 0 ? 256 / TP : 1);
+  if (d.whole_sm_ctas) {  // 512 threads at 128 registers (double) fill an SM
+    const int w512 = 512 / TP > 0 ? 512 / TP : 1;
+    if (w512 > want) want = w512;
+  }
   if (const char *e = getenv(ts ? "P3DFFT_B200_POW2_PENCILS" : "P3DFFT_B200_POW2_PENCILS_PM")) {
     int w = atoi(e);
     if (w > 0) want = w;

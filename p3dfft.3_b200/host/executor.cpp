@@ -137,20 +137,23 @@ static void peer_barrier(Plan *pl, const StagePlan &st, void *stream) {
   GPU(p3dfftcu_peer_barrier(pf, slots, n, ws.flags, pl->rank, ws.epoch, stream), pl, "peer barrier");
 }
 
-// CTA budgets of an overlapped pair: the exchange stage is NVLink-bound and keeps its speed on about half of the SMs
-// (measured on 2 GPUs: 148 -> 74 CTAs costs 3 %), the local stage gets the rest
-static void pair_caps(int *xcap, int *lcap) {
+// CTA budgets of an overlapped pair: the exchange stage is NVLink-bound (SM-issued peer stores top out at 717 GB/s per GPU
+// whatever the run length >= 128 B and from 74 CTAs on: tools/microbench/peer_store_bench.cu) and keeps its speed on about
+// half of the SMs (2 GPUs: 148 -> 74 CTAs costs 3 %); the local stage gets the rest
+static void pair_caps(int npeers, int *xcap, int *lcap) {
   static int sms = p3dfftcu_num_sms();
   static int xs = [] {
     const char *e = getenv("P3DFFT_B200_OVERLAP_XSMS");
     int v = e ? atoi(e) : 0;
     return v > 0 ? v : 0;
   }();
-  int x = xs > 0 ? xs : sms / 2;
+  // measured (1024^3 double): 2 GPUs 74 of 148 SMs best (the local stage is half as long as the exchange); 4 and 8 GPUs,
+  // where the local stage is a third or less of the exchange, ~90-100
+  int x = xs > 0 ? xs : (npeers <= 2 ? sms / 2 : sms * 5 / 8);
   if (x >= sms) x = sms - 1;
   if (x < 1) x = 1;
-  *xcap = x;              // one CTA per SM (the exchange kernels fill an SM's registers)
-  *lcap = 2 * (sms - x);  // the local kernels run two CTAs per SM
+  *xcap = x;        // the chunk stages of a pair are planned with CTAs that fill an SM (whole_sm_ctas): one CTA per SM,
+  *lcap = sms - x;  // so the two kernels can never crowd each other out whatever the dispatch order
 }
 
 // runs stages s (first) and s+1 of an overlapped pair; `ssrc` = input of stage s, `ldst` = output of the local stage
@@ -166,9 +169,21 @@ static void run_pair(Plan *pl, size_t s, const void *ssrc, void *ldst, const int
   for (size_t q = 0; q < X.peers.size(); q++) xdsts[q] = ws.peer_buf[w][X.peers[q].peer_world];
   void *xstream = pl->xstream;
   std::vector<void *> &ev = pl->sync_events;  // [0] fork, [1] join, [2 + c] chunk c of the first stage is complete
+  // P3DFFT_B200_OVERLAP_TRACE=1: start/end events of every chunk on its stream, printed (rank 0) relative to the fork
+  static const bool trace = getenv("P3DFFT_B200_OVERLAP_TRACE") && atoi(getenv("P3DFFT_B200_OVERLAP_TRACE"));
+  static std::vector<void *> tev;
+  auto mark = [&](size_t i, void *st) {
+    if (!trace) return;
+    while (tev.size() <= i) {
+      void *e = nullptr;
+      GPU(p3dfftcu_event_create(&e), pl, "event");
+      tev.push_back(e);
+    }
+    GPU(p3dfftcu_event_record(tev[i], st), pl, "event");
+  };
   const size_t C = X.chunks.size();
   int xcap, lcap;
-  pair_caps(&xcap, &lcap);
+  pair_caps((int)X.peers.size(), &xcap, &lcap);
   GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
   GPU(p3dfftcu_stream_wait_event(xstream, ev[0]), pl, "stream wait");
   peer_barrier(pl, X, xstream);  // every peer has finished reading its buffer w
@@ -176,37 +191,60 @@ static void run_pair(Plan *pl, size_t s, const void *ssrc, void *ldst, const int
     // main stream: L chunk by chunk into my work buffer; side stream: X on each chunk as soon as it is complete
     void *lbuf = ws.buf[s & 1];
     for (size_t c = 0; c < C; c++) {
+      mark(4 * c + 0, stream);
       if (L.chunks[c].handle) {
         void *d1[1] = {lbuf};
         GPU(p3dfftcu_stage_exec_capped(L.chunks[c].handle, (const char *)ssrc + L.chunks[c].in_off_bytes, d1, 1, gL, stream,
                                        c == 0 ? 0 : lcap), pl, "stage launch");
       }
+      mark(4 * c + 1, stream);
       GPU(p3dfftcu_event_record(ev[2 + c], stream), pl, "event");
       GPU(p3dfftcu_stream_wait_event(xstream, ev[2 + c]), pl, "stream wait");
+      mark(4 * c + 2, xstream);
       if (X.chunks[c].handle)
         GPU(p3dfftcu_stage_exec_capped(X.chunks[c].handle, (const char *)lbuf + X.chunks[c].in_off_bytes, xdsts, (int)X.peers.size(),
                                        gX, xstream, c + 1 == C ? 0 : xcap), pl, "stage launch");
+      mark(4 * c + 3, xstream);
     }
     peer_barrier(pl, X, xstream);  // every peer's blocks have landed in my buffer w
   } else {
     // side stream: X chunk by chunk, each followed by a barrier (chunk c of every peer has landed); main stream: L on
     // each chunk of the received array
     for (size_t c = 0; c < C; c++) {
+      mark(4 * c + 2, xstream);
       if (X.chunks[c].handle)
         GPU(p3dfftcu_stage_exec_capped(X.chunks[c].handle, (const char *)ssrc + X.chunks[c].in_off_bytes, xdsts, (int)X.peers.size(),
                                        gX, xstream, c == 0 ? 0 : xcap), pl, "stage launch");
+      mark(4 * c + 3, xstream);
       peer_barrier(pl, X, xstream);
       GPU(p3dfftcu_event_record(ev[2 + c], xstream), pl, "event");
       GPU(p3dfftcu_stream_wait_event(stream, ev[2 + c]), pl, "stream wait");
+      mark(4 * c + 0, stream);
       if (L.chunks[c].handle) {
         void *d1[1] = {ldst};
         GPU(p3dfftcu_stage_exec_capped(L.chunks[c].handle, (const char *)ws.buf[w] + L.chunks[c].in_off_bytes, d1, 1, gL, stream,
                                        c + 1 == C ? 0 : lcap), pl, "stage launch");
       }
+      mark(4 * c + 1, stream);
     }
   }
   GPU(p3dfftcu_event_record(ev[1], xstream), pl, "event");
   GPU(p3dfftcu_stream_wait_event(stream, ev[1]), pl, "stream wait");
+  if (trace) {
+    mark(4 * C, stream);
+    GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");
+    if (pl->rank == 0) {
+      fprintf(stderr, "pair trace (%s first, %zu chunks, xcap %d lcap %d), ms since fork:", l_first ? "L" : "X", C, xcap, lcap);
+      for (size_t c = 0; c < C; c++) {
+        float t[4];
+        for (int i = 0; i < 4; i++) GPU(p3dfftcu_event_elapsed(ev[0], tev[4 * c + i], &t[i]), pl, "event");
+        fprintf(stderr, "  [%zu] L %.2f-%.2f X %.2f-%.2f", c, t[0], t[1], t[2], t[3]);
+      }
+      float te;
+      GPU(p3dfftcu_event_elapsed(ev[0], tev[4 * C], &te), pl, "event");
+      fprintf(stderr, "  end %.2f\n", te);
+    }
+  }
 }
 
 static void add_timer(const StagePlan &st, bool deriv, double sec) {

@@ -352,6 +352,7 @@ bool make_chunk(const StagePlan &st, int prec, int cdim, int c0, int c1, StagePl
   out->in_off_bytes = 0;
   if (c1 <= c0) return true;
   p3dfftcu_stage_desc d = st.desc;
+  d.whole_sm_ctas = 1;  // the two stages of a pair split the SMs by CTA count
   const bool along_u = cdim == st.u;
   long long in_off;
   if (along_u) {
@@ -374,7 +375,7 @@ bool make_chunk(const StagePlan &st, int prec, int cdim, int c0, int c1, StagePl
 bool plan_overlap(Plan *pl, const std::vector<ProtoStage> &protos) {
   const size_t S = pl->stages.size();
   if (pl->nranks < 2 || S < 2 || !env_int("P3DFFT_B200_OVERLAP", 1)) return true;
-  int nchunks = env_int("P3DFFT_B200_OVERLAP_CHUNKS", 4);
+  int nchunks = env_int("P3DFFT_B200_OVERLAP_CHUNKS", 8);
   if (nchunks < 2) return true;
   if (nchunks > 16) nchunks = 16;
   std::vector<bool> used(S, false);
