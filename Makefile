@@ -34,7 +34,11 @@ $(OBJDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) 
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
 
-$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(PIPEOBJ)
+$(OBJDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(OBJDIR)/fastcore_inst.o $(PIPEOBJ)
 	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static -ldl -lrt -lpthread
 
 emu: $(EMULIB)
@@ -48,7 +52,10 @@ EMUPIPEOBJ := $(PIPEKEYS:%=$(EMUDIR)/pipe_%.o)
 $(EMUDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
 	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
-$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUPIPEOBJ)
+$(EMUDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
+	@mkdir -p $(EMUDIR)
+	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -c $< -o $@
+$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUDIR)/fastcore_inst.o $(EMUPIPEOBJ)
 	$(CXX) -shared -o $@ $^ -lrt -lpthread
 
 clean:

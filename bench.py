@@ -35,7 +35,9 @@ def flops_3d(n):
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clocks and throttle reasons with nvidia-smi while the timed region runs"""
+    """samples SM clocks, power and throttle reasons while the GPU is under load: NVML in-process every 2 ms (nvidia-smi
+    every 100 ms when NVML is unavailable).  Samples are time-stamped so the ones inside the timed region can be told
+    from the warm-up ones; a region shorter than the sampling period falls back to all samples taken under load."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -44,37 +46,73 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
-        self.reasons = set()
+        self.samples = []  # (t, sm_mhz, sm_max_mhz, power_w, [reasons])
         self.proc = None
+        self.halt = threading.Event()
+        self.t0 = self.t1 = None  # timed region
+
+    def _gpu_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self._gpu_index())
+        smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+        while not self.halt.is_set():
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), smax, pw,
+                                 [n for n, b in bits if r & b]))
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                      "-i", str(self._gpu_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
+                      if v.lower().startswith("active")]
+                self.samples.append((time.perf_counter(), float(f[1]), float(f[2]), float(f[3]), rs))
+            except ValueError:
+                continue
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 8:
-                    continue
-                try:
-                    self.samples.append((float(f[1]), float(f[2]), float(f[3])))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(name)
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
 
     def stop(self):
+        self.halt.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(self.reasons),
-                "samples": len(sm), "power_w_max": max(s[2] for s in self.samples)}
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+        use, where = (inside, "timed region") if len(inside) >= 3 else (self.samples, "warm-up + timed region (region shorter than 3 samples)")
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(s[1] for s in use)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[2] for s in use), "reasons": sorted({r for s in use for r in s[4]}),
+                "samples": len(sm), "sampled_during": where, "power_w_max": max(s[3] for s in use)}
 
 
 def measured_peaks():
@@ -274,13 +312,14 @@ def main():
     tol = 1e-5 if single else 1e-12
     assert rt_err < tol, f"round-trip error {rt_err}"
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_device()
     lib.enable_timers(True)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.t0 = time.perf_counter()
     l0 = lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -290,6 +329,7 @@ def main():
         step_device()
     e1.record(stream)
     barrier()
+    sampler.t1 = time.perf_counter()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib.kernel_launches() - l0
     # per-stage durations averaged over the steps of the timed region (CUDA events recorded by the library on the launch

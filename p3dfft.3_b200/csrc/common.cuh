@@ -61,6 +61,9 @@ struct StageParams {
   const void *tw;   // exp(-2 pi i j / L), j < L
   const void *tw2;  // exp(-i pi j / (2 n)), j < 2n   (r2r kinds II-IV)
   const void *tw3;  // exp(-i pi (2k+1) / (4 n)), k < n (r2r kinds IV)
+  const void *tw_core;  // fastcore kernel: exp(-2 pi i j / M) of the power-of-two core
+  const void *chirp;    // Bluestein: c_j = exp(-i pi j^2 / L), j < L
+  const void *bhat;     // Bluestein: FFT_M of the wrapped conj chirp, divided by M
   int deriv_g;      // > 0: spectral derivative epilogue with full length g
   int nseg;
   SegDev seg[P3DFFTCU_MAXSEG];

@@ -19,6 +19,7 @@
 #include "generic_stage.cuh"
 #include "pow2_stage.cuh"
 #include "pow2_pipe.cuh"
+#include "fastcore_stage.cuh"
 
 using namespace p3b;
 
@@ -87,6 +88,72 @@ template <typename T> int build_table(int which, int n, void **out) {
   CK(cudaMalloc(&d, h.size() * sizeof(T)));
   CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = d;
+  return 0;
+}
+
+// Bluestein tables for length L on a power-of-two core of M points (M >= 2L-1):
+//   chirp[j] = exp(-i pi j^2 / L), j < L;  bhat = FFT_M(h) / M with h[i] = h[M-i] = conj(chirp[i]) for i < L, 0 elsewhere
+std::map<std::tuple<int, int, int>, std::pair<void *, void *>> g_blue;
+
+void fft_ld(std::vector<long double> &re, std::vector<long double> &im) {  // in-place radix-2, forward, length 2^k
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; i++) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (size_t len = 2; len <= n; len <<= 1) {
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; k++) {
+        const long double a = -2.0L * pi * (long double)k / (long double)len, wr = cosl(a), wi = sinl(a);
+        const size_t p = i + k, q = i + k + len / 2;
+        const long double xr = re[q] * wr - im[q] * wi, xi = re[q] * wi + im[q] * wr;
+        re[q] = re[p] - xr; im[q] = im[p] - xi;
+        re[p] += xr; im[p] += xi;
+      }
+  }
+}
+
+template <typename T> int build_blue(int L, int M, void **chirp_out, void **bhat_out) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<long double> cr(L), ci(L), hr(M, 0.0L), hi(M, 0.0L);
+  for (int j = 0; j < L; j++) {
+    const long long q = ((long long)j * j) % (2LL * L);  // j^2 mod 2L keeps the argument small
+    const long double a = -pi * (long double)q / (long double)L;
+    cr[j] = cosl(a);
+    ci[j] = sinl(a);
+    hr[j] = cr[j];
+    hi[j] = -ci[j];
+    if (j > 0) { hr[M - j] = cr[j]; hi[M - j] = -ci[j]; }
+  }
+  fft_ld(hr, hi);
+  std::vector<T> hc(2 * (size_t)L), hb(2 * (size_t)M);
+  for (int j = 0; j < L; j++) { hc[2 * j] = (T)cr[j]; hc[2 * j + 1] = (T)ci[j]; }
+  for (int j = 0; j < M; j++) { hb[2 * j] = (T)(hr[j] / M); hb[2 * j + 1] = (T)(hi[j] / M); }
+  void *dc = nullptr, *db = nullptr;
+  CK(cudaMalloc(&dc, hc.size() * sizeof(T)));
+  CK(cudaMemcpy(dc, hc.data(), hc.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&db, hb.size() * sizeof(T)));
+  CK(cudaMemcpy(db, hb.data(), hb.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *chirp_out = dc;
+  *bhat_out = db;
+  return 0;
+}
+
+int get_blue(int L, int M, int prec, const void **chirp, const void **bhat) {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(L, M, prec);
+  auto it = g_blue.find(key);
+  if (it == g_blue.end()) {
+    void *c = nullptr, *b = nullptr;
+    int rc = prec == 8 ? build_blue<double>(L, M, &c, &b) : build_blue<float>(L, M, &c, &b);
+    if (rc) return rc;
+    it = g_blue.emplace(key, std::make_pair(c, b)).first;
+  }
+  *chirp = it->second.first;
+  *bhat = it->second.second;
   return 0;
 }
 
@@ -162,7 +229,7 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
 #endif
 
 // ------------------------------------------------------------------ stage object
-enum Variant { V_GENERIC = 0, V_POW2 = 1, V_PIPE = 2 };
+enum Variant { V_GENERIC = 0, V_POW2 = 1, V_PIPE = 2, V_FAST = 3 };
 
 struct PipePlan {
   const p3b::PipeInfo *info = nullptr;
@@ -170,6 +237,12 @@ struct PipePlan {
   int tile_u = 1, tile_v = 1, tu_log2 = 0, load_ord = 0, store_ord = 0;
   long long tiles_u = 0, tiles_v = 0, ntiles = 0;
   int vfast = 0;
+};
+
+struct FastPlan {
+  p3b::FastInfo info;
+  int M = 0, blue = 0, threads = 0, grid = 0;
+  size_t smem = 0;
 };
 
 }  // namespace
@@ -183,6 +256,7 @@ struct p3dfftcu_stage_s {
   size_t smem;
   Pow2Plan pw;
   PipePlan pp;
+  FastPlan fp;
   bool have_pw = false;  // the non-pipelined pow2 kernel is kept as the fallback for unaligned user pointers
   std::string name;
 };
@@ -277,10 +351,76 @@ template <typename T> int setup_generic(p3dfftcu_stage_s *st) {
 }
 
 
+
 int ilog2(int x) {
   int l = 0;
   while ((1 << l) < x) l++;
   return l;
+}
+
+// fastcore kernel (fastcore_stage.cuh): any kind whose internal FFT length L is a power of two in 64..4096, or any L with
+// 2L-1 <= 4096 through Bluestein; fills st->P's tile shape like the generic kernel.  0 ok, <0 not applicable, >0 error
+int fast_setup(p3dfftcu_stage_s *st) {
+  const p3dfftcu_stage_desc &d = st->d;
+  StageParams &P = st->P;
+  if (d.kind == P3DFFTCU_K_EMPTY) return -1;
+  const int L = P.L;
+  if (L < 24) return -1;  // tiny transforms: the generic kernel's direct butterflies are as good
+  int M = 64, blue = 0;
+  if ((L & (L - 1)) == 0 && L >= 64 && L <= 4096) M = L;
+  else {
+    blue = 1;
+    while (M < 2 * L - 1) M *= 2;
+    if (M > 4096) return -1;
+  }
+  FastPlan &fp = st->fp;
+  if (!fast_lookup(d.prec, M, blue, &fp.info)) return -1;
+  const size_t csz = (size_t)d.prec * 2;
+  const int TP = fp.info.tp;
+  int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
+  int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
+  const bool needU = fin == 1 || fout == 1, needV = fin == 2 || fout == 2;
+  // pencils per tile: 128-byte runs across pencils when a side is transposed (as many as 512 threads and the shared
+  // memory hold, at most 16); 256-thread CTAs otherwise, so that two or three of them overlap their phases on an SM
+  int np = (needU || needV) ? 512 / TP : 256 / TP;
+  if (np > 16) np = 16;
+  if (np < 1) np = 1;
+  while (np > 1 && ((size_t)np * fp.info.pitch + fp.info.table_elems) * csz > g_smem_optin - 1024) np /= 2;
+  if (((size_t)np * fp.info.pitch + fp.info.table_elems) * csz > g_smem_optin - 1024) return -1;
+  if (np * TP < 32) return -1;
+  int tu = np, tv = 1;
+  if (needU && needV) {
+    tu = 1;
+    while (tu * tu < np) tu *= 2;
+    tv = np / tu;
+  } else if (needV) {
+    tv = np;
+    tu = 1;
+  }
+  P.tile_u = tu;
+  P.tile_v = tv;
+  P.tu_log2 = ilog2(tu);
+  P.load_ord = fin == 0 ? ORD_D : (fin == 1 ? ORD_U : ORD_V);
+  P.store_ord = fout == 0 ? ORD_D : (fout == 1 ? ORD_U : ORD_V);
+  P.tiles_u = (d.nu + tu - 1) / tu;
+  P.ntiles = P.tiles_u * ((d.nv + tv - 1) / tv);
+  if (get_table(0, M, d.prec, &P.tw_core)) return 1;
+  if (blue && get_blue(L, M, d.prec, &P.chirp, &P.bhat)) return 1;
+  fp.M = M;
+  fp.blue = blue;
+  fp.threads = np * TP;
+  fp.smem = ((size_t)np * fp.info.pitch + fp.info.table_elems) * csz;
+  if (cudaFuncSetAttribute(fp.info.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smem) != cudaSuccess) return 1;
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp.info.func, fp.threads, fp.smem) != cudaSuccess) return 1;
+  if (occ < 1) occ = 1;
+  long long g = (long long)g_num_sms * occ;
+  fp.grid = (int)(P.ntiles < g ? (P.ntiles > 0 ? P.ntiles : 1) : g);
+  char nm[200];
+  snprintf(nm, sizeof nm, "fastcore<%s,L=%d,M=%d%s> threads=%d tile=%dx%d load=%d store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", L, M, blue ? ",bluestein" : "", fp.threads, tu, tv, P.load_ord, P.store_ord, fp.smem, fp.grid, occ);
+  st->name = nm;
+  return 0;
 }
 
 // picks the pipelined kernel (pow2_pipe.cuh) for a stage; returns 0 ok, <0 not applicable, >0 CUDA error
@@ -477,6 +617,14 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) 
         }
       }
     }
+    if (!rc && st->variant == V_GENERIC && allow_fast) {  // r2r kinds, other lengths: the register core (+ Bluestein)
+      const char *nofast = getenv("P3DFFT_B200_NO_FASTCORE");
+      if (!(nofast && atoi(nofast))) {
+        int frc = fast_setup(st);
+        if (frc > 0) rc = failmsg("fastcore stage kernel setup failed");
+        else if (frc == 0) st->variant = V_FAST;
+      }
+    }
     if (!rc && st->variant == V_GENERIC) rc = d.prec == 8 ? setup_generic<double>(st) : setup_generic<float>(st);
   }
   if (rc) {
@@ -509,7 +657,7 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
     if (slot < 0 || slot >= ndst || !dst[slot]) return failmsg("stage: missing destination buffer for a segment");
     P.seg[s].base = dst[slot];
   }
-  if (P.ntiles == 0 && st->variant == V_GENERIC) return 0;  // (the generic plan's tile count; other variants carry their own)
+  if (P.ntiles == 0 && (st->variant == V_GENERIC || st->variant == V_FAST)) return 0;  // (the generic plan's tile count; other variants carry their own)
   cudaStream_t cs = (cudaStream_t)stream;
   Variant variant = st->variant;
   if (variant == V_PIPE) {
@@ -529,6 +677,13 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
       }
       if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
       pp.info->launch(P, grid, cs);
+    }
+  } else if (variant == V_FAST) {
+    const FastPlan &fp = st->fp;
+    if (P.ntiles > 0) {
+      int grid = fp.grid;
+      if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+      fp.info.launch(P, grid, fp.threads, fp.smem, cs);
     }
   } else if (variant == V_POW2) {
     Pow2Plan pw = st->pw;

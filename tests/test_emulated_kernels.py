@@ -6,7 +6,7 @@ library is exercised by tests/test_gpu_parity.py (-m gpu)."""
 import numpy as np
 import pytest
 
-from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
+from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, FASTCORE_CASES, PERMS, R2R_KINDS, RCC, RCC_S, half
 from util import TOL, check_golden, run_1d, run_3d
 
 
@@ -97,6 +97,29 @@ def test_r2r_kinds_1d(emu, orc, kind, variant, monkeypatch):
     for dim, n in ((0, (9, 4, 3)), (1, (3, 12, 2)), (2, (2, 3, 7))):
         assert run_1d(emu, orc, n, name, dim, (0, 1, 2), (0, 1, 2)) < tol
     assert run_1d(emu, orc, (5, 6, 129 if kind == "DCT1" else 16), name, 2, (0, 1, 2), (2, 0, 1)) < tol
+
+
+@pytest.mark.parametrize("name,n", FASTCORE_CASES)
+def test_fastcore_kinds_and_bluestein(emu, orc, name, n):
+    """r2r kinds and non-power-of-two lengths on the register FFT core (fastcore_stage.cuh), transform dimension leading,
+    strided, and with a transposing output order"""
+    tol = TOL[4] if name.endswith("_S") else TOL[8]
+    assert run_1d(emu, orc, (n, 3, 2), name, 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
+    assert run_1d(emu, orc, (3, n, 2), name, 1, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
+    assert run_1d(emu, orc, (2, 5, n), name, 2, (0, 1, 2), (2, 0, 1), expect_variant="fastcore") < tol
+
+
+def test_fastcore_in_3d_with_derivative(emu, orc):
+    """config C4's shape in small: R2C(x), C2C(y), DCT-I(z) with z = 2^k+1 (core directly) and 2^k (Bluestein)"""
+    t = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
+    for nz in (33, 32):
+        n = (16, 12, nz)
+        assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+        assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=2) < TOL[8]
+    assert run_3d(emu, orc, (100, 12, 10), (100, 12, 10), CCC, (0, 1, 2), (2, 1, 0)) < TOL[8]
+    n = (90, 40, 26)  # Bluestein R2C / C2R (Hermitian extension) round the 3D transform
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+    assert run_3d(emu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
 
 
 @pytest.mark.parametrize("mo1", PERMS)

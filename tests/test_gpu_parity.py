@@ -5,7 +5,7 @@ pure permutations must be bit-exact."""
 import numpy as np
 import pytest
 
-from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
+from cases import FASTCORE_CASES, CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
 from util import TOL, check_golden, run_1d, run_3d
 
 pytestmark = pytest.mark.gpu
@@ -97,6 +97,31 @@ def test_r2r_kinds(gpu, orc, kind, variant):
     for dim, n in ((0, (129, 14, 6)), (1, (12, 64, 5)), (2, (6, 9, 100))):
         for mo1, mo2 in (((0, 1, 2), (0, 1, 2)), ((0, 1, 2), (2, 0, 1)), ((1, 2, 0), (0, 1, 2))):
             assert run_1d(gpu, orc, n, name, dim, mo1, mo2) < tol
+
+
+@pytest.mark.parametrize("name,n", FASTCORE_CASES + [("DCT1_COMPLEX_D", 513), ("DCT1_COMPLEX_D", 512), ("DST1_REAL_D", 1023),
+                                                     ("DCT2_COMPLEX_D", 1024), ("DST3_REAL_S", 600), ("CFFT_FORWARD_D", 1000),
+                                                     ("CFFT_BACKWARD_D", 768), ("R2CFFT_D", 1000), ("CFFT_FORWARD_S", 2000),
+                                                     ("CFFT_FORWARD_D", 2048 - 1)])
+def test_fastcore_kinds_and_bluestein(gpu, orc, name, n):
+    """r2r kinds and non-power-of-two lengths on the register FFT core (fastcore_stage.cuh): core sizes 64...4096,
+    directly (L a power of two) and through Bluestein; leading, strided and transposing layouts"""
+    tol = TOL[4] if name.endswith("_S") else TOL[8]
+    assert run_1d(gpu, orc, (n, 5, 3), name, 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
+    assert run_1d(gpu, orc, (9, n, 2), name, 1, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
+    assert run_1d(gpu, orc, (2, 17, n), name, 2, (0, 1, 2), (2, 0, 1), expect_variant="fastcore") < tol
+
+
+def test_fastcore_3d_c4_literal_and_bluestein_real(gpu, orc):
+    """config C4 with z = 128 (L = 254 = 2*127: Bluestein) and 129 (L = 256), derivative; R2C/C2R of length 90"""
+    t = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
+    for nz in (129, 128):
+        n = (64, 48, nz)
+        assert run_3d(gpu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+        assert run_3d(gpu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=2) < TOL[8]
+    n = (90, 40, 26)
+    assert run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+    assert run_3d(gpu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
 
 
 @pytest.mark.parametrize("mo1", PERMS)

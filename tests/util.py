@@ -68,7 +68,7 @@ def run_3d(lib, orc, gdims1, gdims2, types, mo1, mo2, dmap1=(0, 1, 2), dmap2=(0,
     return err
 
 
-def run_1d(lib, orc, gdims, type_name, dim, mo1, mo2, key=7):
+def run_1d(lib, orc, gdims, type_name, dim, mo1, mo2, key=7, expect_variant=None):
     """transplan-style 1D transform (p3dfft_plan_1Dtrans) on one rank"""
     kind, dt_in, dt_out, prec = orc.type_info(type_name)
     single = prec == 4
@@ -81,6 +81,8 @@ def run_1d(lib, orc, gdims, type_name, dim, mo1, mo2, key=7):
     plan = lib.plan_1Dtrans(g1, g2, type_name, dim)
     desc = lib.describe_plan1d(plan)
     assert desc["ok"], desc
+    if expect_variant:
+        assert any(s["variant"].startswith(expect_variant) for s in desc["stages"]), [s["variant"] for s in desc["stages"]]
     G = orc.random_field(gdims, complex_=(dt_in == 2), key=key)
     og1 = orc.OGrid(gdims, [0, 1, 2], mo1, [1, 1, 1], 0)
     og2 = orc.OGrid(gd2, [0, 1, 2], mo2, [1, 1, 1], 0)

@@ -33,6 +33,7 @@ extern pthread_barrier_t emu_block_barrier;
 inline void __syncthreads() { pthread_barrier_wait(&emu_block_barrier); }
 inline void __syncwarp() { pthread_barrier_wait(&emu_block_barrier); }  // callers are uniform across the CTA
 template <class T> inline T __ldg(const T *p) { return *p; }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 using std::max;
 using std::min;
 
