@@ -410,7 +410,8 @@ int fast_setup(p3dfftcu_stage_s *st) {
   fp.blue = blue;
   fp.threads = np * TP;
   fp.smem = ((size_t)np * fp.info.pitch + fp.info.table_elems) * csz;
-  if (cudaFuncSetAttribute(fp.info.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smem) != cudaSuccess) return 1;
+  // one kernel function serves stages with different pencils per tile: allow the largest request once and for all
+  if (cudaFuncSetAttribute(fp.info.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem_optin) != cudaSuccess) return 1;
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fp.info.func, fp.threads, fp.smem) != cudaSuccess) return 1;
   if (occ < 1) occ = 1;
@@ -433,7 +434,13 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   if (fin != 0 || d.is_d != 1) return -1;  // bulk copies move whole pencils: the transform dimension must be unit-stride
   // 16-byte aligned pencils of a multiple of 16 bytes.  esz = bytes of one input element
   const long long esz = (long long)d.prec * d.dt_in;
-  if ((d.is_u * esz) % 16 || (d.is_v * esz) % 16 || ((long long)d.n_in * esz) % 16) return -1;
+  if ((d.is_u * esz) % 16 || (d.is_v * esz) % 16) return -1;
+  if (((long long)d.n_in * esz) % 16) {
+    // single-precision C2R (M+1 elements of 8 bytes): the copy takes one element more, which must belong to the array:
+    // true when the rows are padded (library-owned intermediates, planner.cpp) so that every pencil is followed by a gap
+    const bool roomy = (d.nu <= 1 || d.is_u > d.n_in) && (d.nv <= 1 || d.is_v > d.n_in);
+    if (!(d.kind == P3DFFTCU_K_C2R && d.prec == 4 && roomy)) return -1;
+  }
   const int ts = fout != 0;
   const size_t csz = (size_t)d.prec * 2;
   const int E = M == 64 ? 8 : 16, TP = M / E;

@@ -76,7 +76,9 @@ constexpr size_t kPipeSmemMax = 232448 - 1024;  // 227 KB opt-in minus the stati
 template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
   enum { E = Pow2Cfg<M>::E, TP = M / E, THREADS = P * TP, XP0 = Pow2Smem<M>::PENCIL };
   enum { R1 = Pow2Cfg<M>::R1, R2 = Pow2Cfg<M>::R2, R3 = Pow2Cfg<M>::R3 };
-  enum { NIN = KIND == P3DFFTCU_K_C2R ? M + 1 : M };  // complex-sized elements of one pencil landing in shared memory
+  // complex-sized elements of one pencil landing in shared memory; a bulk copy moves multiples of 16 bytes, so the M+1
+  // single-precision elements of a C2R pencil travel with the 8 bytes that follow them (the host checks they exist)
+  enum { NIN = KIND == P3DFFTCU_K_C2R ? (sizeof(T) == 4 ? M + 2 : M + 1) : M };
   static constexpr size_t csz = 2 * sizeof(T);
   // pencil pitch (complex elements): every pencil starts 16-byte aligned (bulk-copy destination) an odd number of
   // 16-byte units after the previous one, so the lanes-across-pencils accesses of the transposed mapping spread over

@@ -143,7 +143,7 @@ void DataGrid::InitPencil() {
 
 namespace b200 {
 
-void Layout::set(const int ld[3], const int mo_[3]) {
+void Layout::set(const int ld[3], const int mo_[3], int pad_elems) {
   int imo[3];
   for (int i = 0; i < 3; i++) {
     ldims[i] = ld[i];
@@ -153,8 +153,12 @@ void Layout::set(const int ld[3], const int mo_[3]) {
   long long s = 1;
   for (int r = 0; r < 3; r++) {
     stride[imo[r]] = s;
-    s *= ld[imo[r]];
+    long long ext = ld[imo[r]];
+    // pad rows of at least 4 pad units (waste <= 25 %) that are not already whole units
+    if (r == 0 && pad_elems > 1 && ext >= 4LL * pad_elems && ext % pad_elems) ext = (ext + pad_elems - 1) / pad_elems * pad_elems;
+    s *= ext;
   }
+  span = s;
 }
 
 }  // namespace b200

@@ -17,7 +17,11 @@ struct Layout {
   int mo[3];  // MemOrder: storage rank of logical dim i
   long long stride[3];
   long long count() const { return (long long)ldims[0] * ldims[1] * ldims[2]; }
-  void set(const int ld[3], const int mo_[3]);
+  long long span;  // elements from the first to one past the last, padding included
+  // pad_elems > 0 (library-owned intermediate arrays only): the rows along the unit-stride dimension start every
+  // multiple of pad_elems elements (128 bytes), so that 513-element rows of a half-complex array stay sector- and
+  // bulk-copy-aligned; user-visible arrays are always dense
+  void set(const int ld[3], const int mo_[3], int pad_elems = 0);
 };
 
 struct PeerSeg {

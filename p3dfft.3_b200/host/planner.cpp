@@ -266,7 +266,16 @@ double choose_layouts(const std::vector<ProtoStage> &ps, const int mo1[3], const
   return bestc;
 }
 
-void fill_stage(StagePlan &st, const ProtoStage &p, const int mo_in[3], const int mo_out[3], const ProcGrid *pg, int prec) {
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+void fill_stage(StagePlan &st, const ProtoStage &p, const int mo_in[3], const int mo_out[3], const ProcGrid *pg, int prec,
+                bool inter_in, bool inter_out) {
+  // intermediate (library-owned) arrays get 128-byte aligned rows; P3DFFT_B200_NO_PAD=1 keeps them dense
+  const bool padding = !env_int("P3DFFT_B200_NO_PAD", 0);
+  const int pad_in = (inter_in && padding) ? 128 / (p.dt_in * prec) : 0, pad_out = (inter_out && padding) ? 128 / (p.dt_out * prec) : 0;
   st.kind = p.kind;
   st.dim = p.dim;
   st.u = (p.dim + 1) % 3;
@@ -281,10 +290,10 @@ void fill_stage(StagePlan &st, const ProtoStage &p, const int mo_in[3], const in
   st.xdim_gather = p.xb;
   st.comm_dim = p.comm_dim;
   st.ref_kind = p.exchange ? (p.kind == P3DFFTCU_K_EMPTY ? MPI_ONLY : TRANSMPI) : TRANS_ONLY;
-  st.in.set(p.ld_in, mo_in);
-  st.out.set(p.ld_out, mo_out);
-  st.in_bytes = st.in.count() * p.dt_in * prec;
-  st.out_bytes = st.out.count() * p.dt_out * prec;
+  st.in.set(p.ld_in, mo_in, pad_in);
+  st.out.set(p.ld_out, mo_out, pad_out);
+  st.in_bytes = st.in.span * p.dt_in * prec;
+  st.out_bytes = st.out.span * p.dt_out * prec;
   p3dfftcu_stage_desc &d = st.desc;
   memset(&d, 0, sizeof d);
   d.kind = p.kind;
@@ -327,7 +336,7 @@ void fill_stage(StagePlan &st, const ProtoStage &p, const int mo_in[3], const in
     ps.k1 = kst + ksz;
     int ldq[3] = {p.ld_out[0], p.ld_out[1], p.ld_out[2]};
     ldq[p.dim] = ksz;
-    ps.lay.set(ldq, mo_out);
+    ps.lay.set(ldq, mo_out, pad_out);
     ps.b_off = b_st;
     st.peers.push_back(ps);
     d.seg[q].k0 = ps.k0;
@@ -341,10 +350,6 @@ void fill_stage(StagePlan &st, const ProtoStage &p, const int mo_in[3], const in
 }
 
 // ---- overlap pairs: cut an exchange stage X and a neighbouring local stage L into the same chunks
-int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 
 // chunk [c0, c1) of stage st along logical dimension cdim (one of st.u, st.v)
 bool make_chunk(const StagePlan &st, int prec, int cdim, int c0, int c1, StagePlan::Chunk *out, std::string *err) {
@@ -448,7 +453,7 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
   for (size_t s = 0; s < S; s++) {
     const int *mi = s == 0 ? mo1 : kPerm[perm[s]];
     const int *mo = s + 1 == S ? mo2 : kPerm[perm[s + 1]];
-    fill_stage(pl->stages[s], protos[s], mi, mo, pl->pgrid, pl->prec);
+    fill_stage(pl->stages[s], protos[s], mi, mo, pl->pgrid, pl->prec, s > 0, s + 1 < S);
     if (pl->stages[s].desc.nseg > P3DFFTCU_MAXSEG) {
       pl->error = "too many ranks in one exchange sub-communicator for this build (max 32)";
       return false;
