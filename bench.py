@@ -49,6 +49,7 @@ class ClockSampler(threading.Thread):
         self.samples = []  # (t, sm_mhz, sm_max_mhz, power_w, [reasons])
         self.proc = None
         self.halt = threading.Event()
+        self.ready = threading.Event()  # first sample taken (NVML initialisation can take longer than a short timed region)
         self.t0 = self.t1 = None  # timed region
 
     def _gpu_index(self):
@@ -76,6 +77,7 @@ class ClockSampler(threading.Thread):
                 pw = 0.0
             self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), smax, pw,
                                  [n for n, b in bits if r & b]))
+            self.ready.set()
             time.sleep(0.002)
 
     def _run_smi(self):
@@ -89,6 +91,7 @@ class ClockSampler(threading.Thread):
                 rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
                       if v.lower().startswith("active")]
                 self.samples.append((time.perf_counter(), float(f[1]), float(f[2]), float(f[3]), rs))
+                self.ready.set()
             except ValueError:
                 continue
 
@@ -315,6 +318,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.ready.wait(10)
     for _ in range(args.warmup):
         step_device()
     lib.enable_timers(True)
