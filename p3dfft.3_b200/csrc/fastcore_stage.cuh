@@ -20,22 +20,22 @@
 namespace p3b {
 
 // forward FFT core of M points on the E register values of the TP threads of one pencil; exchanges go through the
-// pencil's padded buffer Bp; every thread of the CTA calls this (barriers are CTA-wide).  In: v[m] = x[t + m TP];
+// pencil's padded buffer Bp; `sync` is a barrier over (at least) the threads of the pencil.  In: v[m] = x[t + m TP];
 // out: v[m] = X[t + m TP].  The caller guarantees that nobody still reads Bp.
-template <typename T, int M>
+template <typename T, int M, typename Sync>
 __device__ __forceinline__ void fast_core(typename cx<T>::type *v, int t, typename cx<T>::type *Bp, const typename cx<T>::type *T2,
-                                          const typename cx<T>::type *T3, const typename cx<T>::type *tw) {
+                                          const typename cx<T>::type *T3, const typename cx<T>::type *tw, Sync sync) {
   typedef Pow2Cfg<M> R;
   constexpr int E = R::E, R1 = R::R1, R2 = R::R2, R3 = R::R3;
   reg_pass<T, M, E, R1, false>(v, t, 1, tw, 1);
   smem_scatter<T, M, E, R1>(v, Bp, t, 1);
-  __syncthreads();
+  sync();
   smem_gather<T, M, E>(v, Bp, t);
   reg_pass2<T, M, E, R1, R2>(v, t, T2);
   if constexpr (R3 > 1) {
-    __syncthreads();
+    sync();
     smem_scatter<T, M, E, R2>(v, Bp, t, R1);
-    __syncthreads();
+    sync();
     smem_gather<T, M, E>(v, Bp, t);
     reg_pass3<T, M, E, R3>(v, t, T3);
   }
@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(512) fastcore_stage_kernel(const __grid_consta
   C *Bp = buf0 + slot * PITCH;
   const bool bwd = (P.kind == P3DFFTCU_K_C2C_BWD || P.kind == P3DFFTCU_K_C2R);
   __syncthreads();
+  // when input and output are both unit-stride along the transform dimension every phase of a pencil is done by its own
+  // TP threads: barriers then span that group only (whole warps), and the pencils of a CTA drift apart and overlap their
+  // load / shared-memory / FP64 / store phases; otherwise the gather or the scatter crosses pencils and the CTA synchronises
+  const bool grouped = P.load_ord == ORD_D && P.store_ord == ORD_D && TP >= 32 && NP <= 15;
+  auto sync = [&]() {
+    if (grouped) {
+      if (TP == 32) __syncwarp();
+      else group_bar(1 + slot, TP);
+    } else __syncthreads();
+  };
 
   for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     const long long u0 = (tile % P.tiles_u) * P.tile_u;
@@ -82,14 +92,12 @@ __global__ void __launch_bounds__(512) fastcore_stage_kernel(const __grid_consta
     const int cu = (int)min((long long)P.tile_u, P.nu - u0);
     const int cv = (int)min((long long)P.tile_v, P.nv - v0);
 
-    // ---- zero-fill positions that no input element maps to
-    if (P.kind == P3DFFTCU_K_DST1 || P.kind == P3DFFTCU_K_DCT3 || P.kind == P3DFFTCU_K_DST3) {
-      for (int p = tid; p < NP; p += nth) {
-        C z = mk<T>(0, 0);
-        if (P.kind == P3DFFTCU_K_DST1) { buf0[p * PITCH] = z; buf0[p * PITCH + n + 1] = z; }
-        else if (P.kind == P3DFFTCU_K_DCT3) buf0[p * PITCH + n] = z;
-        else buf0[p * PITCH] = z;
-      }
+    // ---- zero-fill positions that no input element maps to (each pencil by its own first thread)
+    if (t == 0 && (P.kind == P3DFFTCU_K_DST1 || P.kind == P3DFFTCU_K_DCT3 || P.kind == P3DFFTCU_K_DST3)) {
+      const C z = mk<T>(0, 0);
+      if (P.kind == P3DFFTCU_K_DST1) { Bp[0] = z; Bp[n + 1] = z; }
+      else if (P.kind == P3DFFTCU_K_DCT3) Bp[n] = z;
+      else Bp[0] = z;
     }
     // ---- gather + pre-processing
     const int nin = P.n_in;
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(512) fastcore_stage_kernel(const __grid_consta
       }
     }
     }
-    __syncthreads();
+    sync();
 
 
     // ---- length-L FFT of every pencil of the tile on the register core
@@ -171,27 +179,27 @@ __global__ void __launch_bounds__(512) fastcore_stage_kernel(const __grid_consta
         }
         v[m] = x;
       }
-      __syncthreads();  // everything is in registers: the buffers now carry the exchanges
-      fast_core<T, M>(v, t, Bp, T2, T3, twc);
+      sync();  // everything is in registers: the buffers now carry the exchanges
+      fast_core<T, M>(v, t, Bp, T2, T3, twc, sync);
       if (BLUE) {
         // pointwise product with the chirp spectrum, inverse FFT by the conjugation trick (1/M is folded into bhat)
 #pragma unroll
         for (int m = 0; m < E; m++) v[m] = cconj(cmul(v[m], __ldg(&bhat[t + m * TP])));
-        __syncthreads();
-        fast_core<T, M>(v, t, Bp, T2, T3, twc);
+        sync();
+        fast_core<T, M>(v, t, Bp, T2, T3, twc, sync);
 #pragma unroll
         for (int m = 0; m < E; m++) {
           const int k = t + m * TP;
           if (k < L) v[m] = cmul(cconj(v[m]), __ldg(&chirp[k]));
         }
       }
-      __syncthreads();  // the last exchange has been read back
+      sync();  // the last exchange has been read back
 #pragma unroll
       for (int m = 0; m < E; m++) {
         const int k = t + m * TP;
         if (!BLUE || k < L) Bp[k] = bwd ? cconj(v[m]) : v[m];
       }
-      __syncthreads();
+      sync();
     }
 
     // ---- post-processing + scatter
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(512) fastcore_stage_kernel(const __grid_consta
       store_out<T>(P, k, u0 + pu, v0 + pv, y);
     }
     }
-    __syncthreads();
+    sync();
   }
 }
 

@@ -315,7 +315,9 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
     // ---------------- epilogue + stores
     if constexpr (r2c) {
       // X[k] = ((Z[k] + conj Z[M-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[M-k])) / 2, k = 0..M
-      syncB();
+      // (no barrier before these writes: a thread overwrites exactly the locations its own gather above has read.
+      //  Tried and dropped: FFT + split in the pencil-major mapping with partners by warp shuffles and a re-mapping pass
+      //  afterwards -- two CTA barriers instead of three, but 64 double shuffles and spills: 3.85 vs 4.6-4.9 TB/s)
 #pragma unroll
       for (int m = 0; m < E; m++) BB[padidx(tB + m * TP)] = v[m];
       syncB();

@@ -46,3 +46,47 @@ def test_exec_without_device_fails_loudly(pkg):
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert "HAVE False" in out.stdout, (out.stdout, out.stderr)
+
+
+def test_headline_plan_layouts_plan_only():
+    """planner regression at full size without a device (P3DFFT_B200_PLAN_ONLY): 1024^3 R2C / C2R stage list, the storage
+    orders of the intermediates (contiguous loads, transposed stores kept within few pages) and the 128-byte row padding of
+    library-owned half-complex arrays"""
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+sys.path.insert(0, %r)
+import __graft_entry__ as ge
+lib = ge.load_package().Library().setup()
+n = (1024, 1024, 1024)
+pg = lib.init_proc_grid([1, 1, 1])
+g1 = lib.init_data_grid(n, -1, pg, [0, 1, 2], [0, 1, 2])
+g2 = lib.init_data_grid((513, 1024, 1024), 0, pg, [1, 2, 0], [1, 2, 0])
+out = []
+for t, a, b in ((["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], g1, g2), (["C2RFFT_D", "CFFT_BACKWARD_D", "CFFT_BACKWARD_D"], g2, g1)):
+    out.append(lib.describe_plan3d(lib.plan_3Dtrans(a, b, lib.init_3Dtype(t))))
+print("PLANS" + json.dumps(out))
+''' % ROOT
+    env = dict(os.environ, P3DFFT_B200_PLAN_ONLY="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    line = [x for x in r.stdout.splitlines() if x.startswith("PLANS")]
+    assert line, (r.stdout[-2000:], r.stderr[-2000:])
+    fwd, bwd = json.loads(line[0][5:])
+    assert fwd["ok"] and bwd["ok"]
+    assert [s["dim"] for s in fwd["stages"]] == [0, 1, 2] and [s["dim"] for s in bwd["stages"]] == [2, 1, 0]
+    assert [s["kind"] for s in fwd["stages"]] == [3, 1, 1] and [s["kind"] for s in bwd["stages"]] == [2, 2, 4]
+    # forward: [z][y][x] -> [z][kx][y] -> [kx][ky][z] -> [ky][kx][kz]
+    assert [s["out_mo"] for s in fwd["stages"]] == [[1, 0, 2], [2, 1, 0], [1, 2, 0]]
+    # backward: [ky][kx][kz] -> [kx][z][ky] -> [z][y][kx] -> [z][y][x]
+    assert [s["out_mo"] for s in bwd["stages"]] == [[2, 0, 1], [0, 1, 2], [0, 1, 2]]
+    # every stage reads whole pencils (unit stride along its transform dimension)
+    for p in (fwd, bwd):
+        for s in p["stages"]:
+            assert s["in_stride"][s["dim"]] == 1, s
+    # the intermediate [z][y][kx] array of the backward transform has 513-element rows: padded to 520 (128-byte multiple)
+    assert bwd["stages"][2]["in_stride"] == [1, 520, 520 * 1024]
+    assert bwd["stages"][1]["segs"][0]["os_d"] == 520
+    # user-visible arrays stay dense
+    assert fwd["stages"][0]["in_stride"] == [1, 1024, 1024 * 1024] and bwd["stages"][0]["in_stride"] == [1024, 513 * 1024, 1]

@@ -5,7 +5,10 @@ mkdir -p gpurun_out
 : > gpurun_out/xgrid_$N.txt
 for G in ${XGRIDS:-off 74:4 74:8}; do
   unset P3DFFT_B200_OVERLAP P3DFFT_B200_OVERLAP_XSMS P3DFFT_B200_OVERLAP_CHUNKS P3DFFT_B200_OVERLAP_TRACE
-  if [ "$G" = off ]; then export P3DFFT_B200_OVERLAP=0; else
+  unset P3DFFT_B200_XGRID
+  if [ "$G" = off ]; then export P3DFFT_B200_OVERLAP=0;
+  elif [[ "$G" == offx* ]]; then export P3DFFT_B200_OVERLAP=0 P3DFFT_B200_XGRID=${G#offx};   # no overlap, exchange stages capped to N CTAs
+  else
     IFS=: read -r XS CH TR <<< "$G"
     export P3DFFT_B200_OVERLAP=1 P3DFFT_B200_OVERLAP_XSMS=$XS P3DFFT_B200_OVERLAP_CHUNKS=$CH
     [ -n "$TR" ] && export P3DFFT_B200_OVERLAP_TRACE=1
