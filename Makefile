@@ -8,11 +8,12 @@ NVCC     := nvcc
 CXX      := g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 CXXFLAGS := -O2 -std=c++17 -fPIC -fno-gnu-unique -Wall -Wno-comment -Iinclude -Iinclude/compat -I$(PKG)/host
-NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fno-gnu-unique -Iinclude -I$(PKG)/csrc
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fno-gnu-unique -Iinclude -I$(PKG)/csrc $(EXTRA_NVFLAGS)
 HOSTSRC  := geometry registry planner executor cwrap minimpi
-OBJDIR   := $(PKG)/lib/obj
+LIBDIR   ?= $(PKG)/lib
+OBJDIR   := $(LIBDIR)/obj
 HOSTOBJ  := $(HOSTSRC:%=$(OBJDIR)/%.o)
-LIB      := $(PKG)/lib/libp3dfft.3.so
+LIB      := $(LIBDIR)/libp3dfft.3.so
 EMUDIR   := tools/cuda_emu/_build
 EMULIB   := $(EMUDIR)/libp3dfft_emu.so
 CUDA_HOME ?= /usr/local/cuda
