@@ -16,7 +16,7 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_longlon
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("P3DFFT_B200_LIB") or os.path.join(_HERE, "lib", "libp3dfft.3.so")  # (override: A/B builds of the same library)
-EMU_LIB_PATH = os.path.join(ROOT, "tools", "cuda_emu", "_build", "libp3dfft_emu.so")
+EMU_LIB_PATH = os.environ.get("P3DFFT_B200_EMU_LIB") or os.path.join(ROOT, "tools", "cuda_emu", "_build", "libp3dfft_emu.so")
 
 
 class Grid(ctypes.Structure):

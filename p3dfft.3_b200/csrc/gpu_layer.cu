@@ -443,7 +443,7 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   }
   const int ts = fout != 0;
   const size_t csz = (size_t)d.prec * 2;
-  const int E = M == 64 ? 8 : 16, TP = M / E;
+  const int E = pow2_values_per_thread(M), TP = M / E;
   // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
   int want = ts ? (int)(128 / csz) : (256 / TP > 0 ? 256 / TP : 1);
   if (d.whole_sm_ctas) {  // 512 threads at 128 registers (double) fill an SM

@@ -101,7 +101,9 @@ template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
   static constexpr bool valid = (THREADS >= 32) && (THREADS <= 1024) && (P <= 16) && (smem <= kPipeSmemMax) && (TS ? P >= 2 : true) &&
                                 (TP > 32 ? P <= 15 : true);
   // register budget as in pow2_stage.cuh: 128 per thread in double, 80 in single
-  enum { BUDGET = sizeof(T) == 8 ? 512 : 768, MINB = (BUDGET / THREADS) < 1 ? 1 : (BUDGET / THREADS) };
+  // register budget as threads per SM: 128 registers per thread in double (16 complex values + temporaries), 80 in single;
+  // twice as many threads when a thread holds 8 values
+  enum { BUDGET = (sizeof(T) == 8 ? 512 : 768) * (E == 8 && M >= 512 ? 2 : 1), MINB = (BUDGET / THREADS) < 1 ? 1 : (BUDGET / THREADS) };
 };
 
 // a * exp(-2 pi i m / 16) for a compile-time m (folds to the cheapest form after unrolling)
@@ -156,7 +158,7 @@ template <typename T, int M, int E, int R>
 __device__ __forceinline__ void reg_pass3(typename cx<T>::type *v, int t, const typename cx<T>::type *T3) {
   typedef typename cx<T>::type C;
   constexpr int TP = M / E, NB = E / R;
-  static_assert(E == 16, "third pass assumes 16 values per thread");
+  static_assert(E == 16 || NB == 1, "the 16th-root factor below assumes 16 values per thread (or a single butterfly)");
 #ifdef P3B_SKELETON
   return;
 #endif

@@ -109,10 +109,27 @@ template <int M> struct Pow2Cfg;  // E elements per thread, radices R1*R2*R3 = M
 template <> struct Pow2Cfg<64>   { enum { E = 8,  R1 = 8,  R2 = 8,  R3 = 1 }; };
 template <> struct Pow2Cfg<128>  { enum { E = 16, R1 = 16, R2 = 8,  R3 = 1 }; };
 template <> struct Pow2Cfg<256>  { enum { E = 16, R1 = 16, R2 = 16, R3 = 1 }; };
+#ifdef P3B_M512_E8  // experiment: 8 values per thread (64 threads per pencil, 64 registers) for twice the warps per SM.
+                    // Measured (1024^3 double): R2C stage 4.23 vs 4.6-4.7 TB/s, C2R 5.27 vs 6.1-6.2 TB/s -> not the default
+template <> struct Pow2Cfg<512>  { enum { E = 8,  R1 = 8,  R2 = 8,  R3 = 8 }; };
+#else
 template <> struct Pow2Cfg<512>  { enum { E = 16, R1 = 16, R2 = 16, R3 = 2 }; };
+#endif
 template <> struct Pow2Cfg<1024> { enum { E = 16, R1 = 16, R2 = 16, R3 = 4 }; };
 template <> struct Pow2Cfg<2048> { enum { E = 16, R1 = 16, R2 = 16, R3 = 8 }; };
 template <> struct Pow2Cfg<4096> { enum { E = 16, R1 = 16, R2 = 16, R3 = 16 }; };
+// values per thread of the M-point core (host side)
+inline int pow2_values_per_thread(int M) {
+  switch (M) {
+    case 64: return Pow2Cfg<64>::E;
+    case 128: return Pow2Cfg<128>::E;
+    case 256: return Pow2Cfg<256>::E;
+    case 512: return Pow2Cfg<512>::E;
+    case 1024: return Pow2Cfg<1024>::E;
+    case 2048: return Pow2Cfg<2048>::E;
+    default: return Pow2Cfg<4096>::E;
+  }
+}
 
 // padded shared-memory index: one pad element after every 16
 __device__ __forceinline__ int padidx(int i) { return i + (i >> 4); }
@@ -439,7 +456,7 @@ inline int pow2_setup(const p3dfftcu_stage_desc &d, int num_sms, size_t smem_opt
   pl->prec = d.prec;
   int rc = d.prec == 8 ? pow2_bind_any<double>(pl, M, want, smem_optin, num_sms) : pow2_bind_any<float>(pl, M, want, smem_optin, num_sms);
   if (rc) return rc;
-  const int E = (M == 64) ? 8 : 16;
+  const int E = pow2_values_per_thread(M);
   const int npb = pl->threads / (M / E);
   int tu = 1, tv = 1;
   if (needU && needV) {
