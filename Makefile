@@ -1,7 +1,7 @@
 # Build of the B200-native P3DFFT++ transform path.
 #   make            -> p3dfft.3_b200/lib/libp3dfft.3.so   (host C++ + sm_100a CUDA layer; the product)
 #   make emu        -> tools/cuda_emu/_build/libp3dfft_emu.so (CPU-thread emulation of the kernels; dev/test tool only)
-#   make samples    -> the reference's own sample programs, compiled UNMODIFIED from REFERENCE against this library
+#   make -C samples -> the reference's own sample programs, compiled UNMODIFIED from REFERENCE against this library
 #   make oracle     -> oracle/_build (C restatement) and, when REFERENCE exists, oracle/_ref (reference host code on shims)
 PKG      := p3dfft.3_b200
 NVCC     := nvcc
