@@ -195,6 +195,14 @@ template <typename T, int E> __device__ __forceinline__ typename cx<T>::type rea
   return mk<T>(wt.x * c + wt.y * s, wt.y * c - wt.x * s);
 }
 
+// R2C split: X[k] = ((Z[k] + conj Z[M-k]) - i w (Z[k] - conj Z[M-k])) / 2 with w = e^{-2 pi i k/N}
+template <typename T, typename C> __device__ __forceinline__ C r2c_split(C zk, C zpartner, C w) {
+  const C zm = cconj(zpartner);
+  const C s = cadd(zk, zm), d = csub(zk, zm);
+  const C e = cmulmi(cmul(d, w));
+  return mk<T>((T)0.5 * (s.x + e.x), (T)0.5 * (s.y + e.y));
+}
+
 // ------------------------------------------------------------------ the kernel
 template <typename T, int M, int KIND, int P, int TS>
 __global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, TS>::THREADS, PipeCfg<T, M, KIND, P, TS>::MINB)
@@ -207,6 +215,11 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   constexpr bool bwd = KIND == P3DFFTCU_K_C2C_BWD || c2r;
   constexpr int twscale = (r2c || c2r) ? 2 : 1;  // the table is exp(-2 pi i j / nfft), nfft = 2M in the real cases
   constexpr unsigned bytes = (unsigned)(Cfg::NIN * Cfg::csz);  // one pencil (R2C: 2M reals = M complex-sized elements)
+  // R2C whose last pass is radix 2 (M = 512, the 1024-point real transform): the thread that owns the butterflies of
+  // column j = t + 32 b (b < 4) also takes those of column M/2 - j, so both Z[k] and its Hermitian partner Z[M-k] come out
+  // of its own registers: no exchange pass for the split (6 instead of 8 shared-memory passes, two barriers fewer), and
+  // the next tile's bulk copy is issued before the last pass instead of after the split
+  constexpr bool r2c_sym = r2c && R3 == 2 && E == 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);  // one mbarrier per pencil: "landed"
   C *B = reinterpret_cast<C *>(smem_raw + Cfg::bar_bytes);
@@ -315,6 +328,58 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
       syncA();
       smem_scatter<T, M, E, R2>(v, BA, tA, R1);
     }
+    if constexpr (r2c_sym) {
+      constexpr int H = M / 2;  // 256
+      syncB();
+      // gather: v[4c + b] = input c of (pair A first / second, pair B first / second) for b < 4
+      const bool special = tB == 0;  // column 0: its mirror column is itself; j = 0 pairs with j' = M/4
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int j = tB + TP * b;
+        const int jp = (special && b == 0) ? H / 2 : H - j;
+        v[b] = BB[padidx(j)];
+        v[4 + b] = BB[padidx(j + H)];
+        v[8 + b] = BB[padidx(jp)];
+        v[12 + b] = BB[padidx(jp + H)];
+      }
+      syncB();  // every value is in registers: the buffers are free for the next tile
+      issue(tile + gridDim.x);
+      const C w3 = T3[TP + tB];  // w_M^t
+      const bool seg1 = Q.nseg == 1 && Q.deriv_g <= 0;
+      const SegDev &sg = Q.seg[0];
+      C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v;
+      auto put = [&](int k, C x) {
+        if (!live) return;
+        if (seg1) st_out(out + (long long)k * sg.os_d, x);
+        else store_out<T>(Q, k, uo, vo, x);
+      };
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int j = tB + TP * b;
+        // last pass: Z[j], Z[j+H] from pair A (twiddle w_M^j), Z[H-j], Z[M-j] from pair B (twiddle w_M^{H-j} = -conj w_M^j)
+        const C wA = mul_w16<T>(w3, b);  // w_M^{t + 32 b} = w_M^t * w_16^b
+        C wB = mk<T>(-wA.x, wA.y);
+        if (special && b == 0) wB = mk<T>((T)0, (T)-1);  // j' = M/4: w_M^{M/4} = -i
+        const C ta = cmul(v[4 + b], wA), tb = cmul(v[12 + b], wB);
+        const C zA1 = cadd(v[b], ta), zA2 = csub(v[b], ta), zB1 = cadd(v[8 + b], tb), zB2 = csub(v[8 + b], tb);
+        // split twiddles e^{-2 pi i k/N}: k = j: wj; M-j: -conj wj; j+H: -i wj; H-j: -i conj wj
+        const C wj = real_twiddle<T, E>(wt, b);
+        if (special && b == 0) {
+          // Z[0], Z[H] (pair A) and Z[M/4], Z[3M/4] (pair B)
+          put(0, mk<T>(zA1.x + zA1.y, (T)0));
+          put(M, mk<T>(zA1.x - zA1.y, (T)0));
+          put(H, r2c_split<T>(zA2, zA2, mk<T>((T)0, (T)-1)));
+          const T h = (T)0.70710678118654752440084436210485;
+          put(H / 2, r2c_split<T>(zB1, zB2, mk<T>(h, -h)));
+          put(H + H / 2, r2c_split<T>(zB2, zB1, mk<T>(-h, -h)));
+        } else {
+          put(j, r2c_split<T>(zA1, zB2, wj));
+          put(M - j, r2c_split<T>(zB2, zA1, mk<T>(-wj.x, wj.y)));
+          put(j + H, r2c_split<T>(zA2, zB1, mk<T>(wj.y, -wj.x)));
+          put(H - j, r2c_split<T>(zB1, zA2, mk<T>(-wj.y, -wj.x)));
+        }
+      }
+    } else {
     syncB();
     smem_gather<T, M, E>(v, BB, tB);  // re-maps to the store side when TS
     if constexpr (!r2c) {
@@ -323,10 +388,13 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
     }
     if constexpr (R3 > 1) reg_pass3<T, M, E, R3>(v, tB, T3);
     else reg_pass2<T, M, E, R1, R2>(v, tB, T2);
+    }
     // v[m] = forward core output F[tB + m*TP] of pencil slotB
 
     // ---------------- epilogue + stores
-    if constexpr (r2c) {
+    if constexpr (r2c_sym) {
+      // (stored above)
+    } else if constexpr (r2c) {
       // X[k] = ((Z[k] + conj Z[M-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[M-k])) / 2, k = 0..M
       // (no barrier before these writes: a thread overwrites exactly the locations its own gather above has read.
       //  Tried and dropped: FFT + split in the pencil-major mapping with partners by warp shuffles and a re-mapping pass

@@ -70,6 +70,20 @@ def test_pow2_real_sizes(emu, orc, m, both_pow2_kernels):
     assert err < TOL[8]
 
 
+def test_r2c_1024_symmetric_last_pass(emu, orc):
+    """the headline's first stage: 1024-point R2C (512-point core whose radix-2 last pass pairs column j with M/2 - j so
+    that the Hermitian split needs no exchange): contiguous and transposed stores, partial tiles, fused derivative
+    (segment-table store path), single precision"""
+    e3 = ["R2CFFT_D", "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_DOUBLE_COMPLEX"]
+    for n, mo2 in (((1024, 3, 2), (0, 1, 2)), ((1024, 9, 3), (1, 0, 2)), ((1024, 4, 16), (2, 1, 0))):
+        err, _, _, desc = run_3d(emu, orc, n, half(n), e3, (0, 1, 2), mo2, cs2=0, return_all=True)
+        assert desc["stages"][0]["variant"].startswith("pipe<f64,M=512"), desc["stages"][0]["variant"]
+        assert err < TOL[8]
+    n = (1024, 16, 4)
+    assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, deriv=0) < TOL[8]
+    assert run_3d(emu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[4]
+
+
 @pytest.mark.parametrize("mo1,mo2", [((0, 1, 2), (1, 2, 0)), ((1, 2, 0), (0, 1, 2)), ((2, 1, 0), (1, 0, 2)), ((0, 2, 1), (2, 0, 1))])
 def test_pow2_strided_and_transposing(emu, orc, mo1, mo2, both_pow2_kernels):
     """fast path with the transform dimension not leading on one or both sides (64 and 128 points)"""
