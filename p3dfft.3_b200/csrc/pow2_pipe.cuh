@@ -215,11 +215,12 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   constexpr bool bwd = KIND == P3DFFTCU_K_C2C_BWD || c2r;
   constexpr int twscale = (r2c || c2r) ? 2 : 1;  // the table is exp(-2 pi i j / nfft), nfft = 2M in the real cases
   constexpr unsigned bytes = (unsigned)(Cfg::NIN * Cfg::csz);  // one pencil (R2C: 2M reals = M complex-sized elements)
-  // R2C whose last pass is radix 2 (M = 512, the 1024-point real transform): the thread that owns the butterflies of
-  // column j = t + 32 b (b < 4) also takes those of column M/2 - j, so both Z[k] and its Hermitian partner Z[M-k] come out
-  // of its own registers: no exchange pass for the split (6 instead of 8 shared-memory passes, two barriers fewer), and
-  // the next tile's bulk copy is issued before the last pass instead of after the split
-  constexpr bool r2c_sym = r2c && R3 == 2 && E == 16;
+  // R2C with a third pass of radix 2, 4 or 8 (M = 512, 1024, 2048: the 1024-, 2048- and 4096-point real transforms): the
+  // last pass works on NS = M/R3 columns; the thread that owns the butterflies of column j = t + TP b (b < NB/2) also takes
+  // those of the mirror column NS - j, so Z[k] = Z[j + NS q] and its Hermitian partner Z[M-k] = Z[(NS-j) + NS (R3-1-q)] both
+  // come out of its own registers: no exchange pass for the split (6 instead of 8 shared-memory passes, two barriers
+  // fewer), and the next tile's bulk copy is issued before the last pass instead of after the split
+  constexpr bool r2c_sym = r2c && E == 16 && (R3 == 2 || R3 == 4 || R3 == 8);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);  // one mbarrier per pencil: "landed"
   C *B = reinterpret_cast<C *>(smem_raw + Cfg::bar_bytes);
@@ -329,22 +330,26 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
       smem_scatter<T, M, E, R2>(v, BA, tA, R1);
     }
     if constexpr (r2c_sym) {
-      constexpr int H = M / 2;  // 256
+      constexpr int NS = M / R3, NB = E / R3, HB = NB / 2;  // columns of the last pass, butterflies per thread, pairs per thread
       syncB();
-      // gather: v[4c + b] = input c of (pair A first / second, pair B first / second) for b < 4
-      const bool special = tB == 0;  // column 0: its mirror column is itself; j = 0 pairs with j' = M/4
+      // gather: for pair b < HB, column A = j = t + TP b and its mirror B = NS - j (thread 0: column 0 pairs with NS/2);
+      // v[(2 b + side) R3 + q] = input q of that column
+      const bool col0 = tB == 0;
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
+      for (int b = 0; b < HB; b++) {
         const int j = tB + TP * b;
-        const int jp = (special && b == 0) ? H / 2 : H - j;
-        v[b] = BB[padidx(j)];
-        v[4 + b] = BB[padidx(j + H)];
-        v[8 + b] = BB[padidx(jp)];
-        v[12 + b] = BB[padidx(jp + H)];
+        const int jp = (col0 && b == 0) ? NS / 2 : NS - j;
+#pragma unroll
+        for (int q = 0; q < R3; q++) {
+          v[(2 * b) * R3 + q] = BB[padidx(j + NS * q)];
+          v[(2 * b + 1) * R3 + q] = BB[padidx(jp + NS * q)];
+        }
       }
       syncB();  // every value is in registers: the buffers are free for the next tile
       issue(tile + gridDim.x);
-      const C w3 = T3[TP + tB];  // w_M^t
+      C w3[R3];  // w_M^{q t}
+#pragma unroll
+      for (int q = 1; q < R3; q++) w3[q] = T3[q * TP + tB];
       const bool seg1 = Q.nseg == 1 && Q.deriv_g <= 0;
       const SegDev &sg = Q.seg[0];
       C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v;
@@ -353,30 +358,45 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         if (seg1) st_out(out + (long long)k * sg.os_d, x);
         else store_out<T>(Q, k, uo, vo, x);
       };
+      const C one = mk<T>((T)1, (T)0);
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
+      for (int b = 0; b < HB; b++) {
         const int j = tB + TP * b;
-        // last pass: Z[j], Z[j+H] from pair A (twiddle w_M^j), Z[H-j], Z[M-j] from pair B (twiddle w_M^{H-j} = -conj w_M^j)
-        const C wA = mul_w16<T>(w3, b);  // w_M^{t + 32 b} = w_M^t * w_16^b
-        C wB = mk<T>(-wA.x, wA.y);
-        if (special && b == 0) wB = mk<T>((T)0, (T)-1);  // j' = M/4: w_M^{M/4} = -i
-        const C ta = cmul(v[4 + b], wA), tb = cmul(v[12 + b], wB);
-        const C zA1 = cadd(v[b], ta), zA2 = csub(v[b], ta), zB1 = cadd(v[8 + b], tb), zB2 = csub(v[8 + b], tb);
-        // split twiddles e^{-2 pi i k/N}: k = j: wj; M-j: -conj wj; j+H: -i wj; H-j: -i conj wj
+        const bool special = col0 && b == 0;
+        C za[R3], zb[R3];
+#pragma unroll
+        for (int q = 0; q < R3; q++) {
+          za[q] = v[(2 * b) * R3 + q];
+          zb[q] = v[(2 * b + 1) * R3 + q];
+        }
+        // last-pass twiddles: column j: w_M^{q j} = w_M^{q t} w_16^{q b}; mirror NS - j: w_R^q conj(w_M^{q j}); column NS/2: w_{2R}^q
+#pragma unroll
+        for (int q = 1; q < R3; q++) {
+          const C wq = mul_w16<T>(w3[q], q * b);
+          za[q] = cmul(za[q], wq);
+          if (special) zb[q] = mul_w16<T>(zb[q], q * (8 / R3));
+          else zb[q] = mul_w16<T>(cmul(zb[q], cconj(wq)), q * (16 / R3));
+        }
+        Radix<T, R3>::run(za);  // Z[j + NS q]
+        Radix<T, R3>::run(zb);  // Z[j' + NS q]
+        // split twiddles e^{-2 pi i k/N}, k = j + NS q: wj w_{2R}^q; the partner row M - k takes -conj of it
         const C wj = real_twiddle<T, E>(wt, b);
-        if (special && b == 0) {
-          // Z[0], Z[H] (pair A) and Z[M/4], Z[3M/4] (pair B)
-          put(0, mk<T>(zA1.x + zA1.y, (T)0));
-          put(M, mk<T>(zA1.x - zA1.y, (T)0));
-          put(H, r2c_split<T>(zA2, zA2, mk<T>((T)0, (T)-1)));
-          const T h = (T)0.70710678118654752440084436210485;
-          put(H / 2, r2c_split<T>(zB1, zB2, mk<T>(h, -h)));
-          put(H + H / 2, r2c_split<T>(zB2, zB1, mk<T>(-h, -h)));
+        if (special) {
+          put(0, mk<T>(za[0].x + za[0].y, (T)0));
+          put(M, mk<T>(za[0].x - za[0].y, (T)0));
+#pragma unroll
+          for (int q = 1; q < R3; q++) put(NS * q, r2c_split<T>(za[q], za[R3 - q], mul_w16<T>(one, q * (8 / R3))));
+          const C wh = real_twiddle<T, 16>(one, 8 / R3);  // e^{-2 pi i (NS/2) / N}
+#pragma unroll
+          for (int q = 0; q < R3; q++)
+            put(NS / 2 + NS * q, r2c_split<T>(zb[q], zb[R3 - 1 - q], mul_w16<T>(wh, q * (8 / R3))));
         } else {
-          put(j, r2c_split<T>(zA1, zB2, wj));
-          put(M - j, r2c_split<T>(zB2, zA1, mk<T>(-wj.x, wj.y)));
-          put(j + H, r2c_split<T>(zA2, zB1, mk<T>(wj.y, -wj.x)));
-          put(H - j, r2c_split<T>(zB1, zA2, mk<T>(-wj.y, -wj.x)));
+#pragma unroll
+          for (int q = 0; q < R3; q++) {
+            const C wk = mul_w16<T>(wj, q * (8 / R3));
+            put(j + NS * q, r2c_split<T>(za[q], zb[R3 - 1 - q], wk));
+            put(M - j - NS * q, r2c_split<T>(zb[R3 - 1 - q], za[q], mk<T>(-wk.x, wk.y)));
+          }
         }
       }
     } else {

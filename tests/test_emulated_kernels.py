@@ -82,6 +82,12 @@ def test_r2c_1024_symmetric_last_pass(emu, orc):
     n = (1024, 16, 4)
     assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, deriv=0) < TOL[8]
     assert run_3d(emu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[4]
+    # radix-4 and radix-8 last passes (2048- and 4096-point real transforms), double and single
+    e3s = ["R2CFFT_S", "EMPTY_TYPE_SINGLE_COMPLEX", "EMPTY_TYPE_SINGLE_COMPLEX"]
+    for nx in (2048, 4096):
+        assert run_3d(emu, orc, (nx, 3, 2), half((nx, 3, 2)), e3, (0, 1, 2), (0, 1, 2), cs2=0) < TOL[8]
+        assert run_3d(emu, orc, (nx, 9, 2), half((nx, 9, 2)), e3, (0, 1, 2), (1, 0, 2), cs2=0) < TOL[8]
+        assert run_3d(emu, orc, (nx, 2, 9), half((nx, 2, 9)), e3s, (0, 1, 2), (2, 1, 0), cs2=0) < TOL[4]
 
 
 @pytest.mark.parametrize("mo1,mo2", [((0, 1, 2), (1, 2, 0)), ((1, 2, 0), (0, 1, 2)), ((2, 1, 0), (1, 0, 2)), ((0, 2, 1), (2, 0, 1))])
