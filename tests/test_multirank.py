@@ -94,6 +94,15 @@ def test_pow2_kernels_with_exchange_segments():
     launch(4, [fwd((128, 64, 4), [1, 2, 2], reps=1), bwd((128, 64, 4), [1, 2, 2], reps=1)], timeout=1500)
 
 
+def test_r2c_1024_with_exchange_segments():
+    """pencil grid: the 1024-point R2C stage (symmetric-column last pass) is itself an exchange stage, so its out-of-order
+    rows go through the per-peer segment table; also as the local stage of an overlapped pair on a slab grid"""
+    n = (1024, 8, 8)
+    launch(4, [fwd(n, [1, 2, 2], reps=1), bwd(n, [1, 2, 2], reps=1)], timeout=1500)
+    launch(2, [fwd(n, [1, 1, 2], reps=1), fwd(n, [1, 1, 2], reps=1, deriv=0)], timeout=1500,
+           env_extra={"P3DFFT_B200_OVERLAP_ALIGN": "1", "P3DFFT_B200_OVERLAP_CHUNKS": "2"})
+
+
 def test_memory_orders_and_derivative_multirank():
     n = (16, 12, 10)
     cs = []
