@@ -258,6 +258,7 @@ struct p3dfftcu_stage_s {
   PipePlan pp;
   FastPlan fp;
   bool have_pw = false;  // the non-pipelined pow2 kernel is kept as the fallback for unaligned user pointers
+  bool empty = false;    // no local pencils on this rank: exec is a no-op
   std::string name;
 };
 
@@ -596,6 +597,18 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) 
     P.seg[s].off = d.seg[s].off; P.seg[s].os_d = d.seg[s].os_d; P.seg[s].os_u = d.seg[s].os_u; P.seg[s].os_v = d.seg[s].os_v;
     P.seg[s].base = nullptr;
   }
+  if (d.nu <= 0 || d.nv <= 0 || d.n_in <= 0) {
+    // this rank holds no pencil of the stage (more ranks than planes along a distributed dimension): nothing to launch
+    st->variant = V_GENERIC;
+    st->threads = 0;
+    st->grid = 0;
+    st->smem = 0;
+    P.ntiles = 0;
+    st->name = "empty (no local pencils)";
+    st->empty = true;
+    *out = st;
+    return 0;
+  }
   int rc = 0;
   if (d.kind != P3DFFTCU_K_EMPTY) {
     factorize(P.L, P.fac, &P.nfac);
@@ -655,6 +668,7 @@ int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int
 
 int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
                                int max_ctas) {
+  if (st->empty) return 0;
   if (deriv_g > 0 && st->d.dt_out != 2) return failmsg("stage: spectral derivative needs complex output");
   StageParams P = st->P;
   P.in = in;

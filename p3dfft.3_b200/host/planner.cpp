@@ -469,13 +469,22 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
   pl->work_bytes = (wmax + 511) & ~511LL;
   pl->stage_ms.assign(S, 0.f);
   if (gpu_ready()) {
-    for (size_t s = 0; s < S; s++) {
+    bool ok = true;
+    for (size_t s = 0; s < S && ok; s++) {
       if (p3dfftcu_stage_create(&pl->stages[s].desc, &pl->stages[s].handle)) {
         pl->error = std::string("stage setup failed: ") + p3dfftcu_last_error();
-        return false;
+        ok = false;
       }
     }
-    if (!plan_overlap(pl, protos)) return false;
+    if (ok && !plan_overlap(pl, protos)) ok = false;
+    // planning is collective: a failure on one rank must fail the plan everywhere instead of leaving the others waiting in
+    // the workspace exchange below
+    int ok_local = ok ? 1 : 0, ok_all = ok_local;
+    MPI_Allreduce(&ok_local, &ok_all, 1, MPI_INT, MPI_MIN, pl->comm);
+    if (!ok_all) {
+      if (ok) pl->error = "stage setup failed on another rank";
+      return false;
+    }
     bool need_ws = S > 1 || pl->nranks > 1;
     for (size_t s = 0; s < S; s++) need_ws = need_ws || pl->stages[s].exchange;
     std::string err;

@@ -94,6 +94,16 @@ def test_pow2_kernels_with_exchange_segments():
     launch(4, [fwd((128, 64, 4), [1, 2, 2], reps=1), bwd((128, 64, 4), [1, 2, 2], reps=1)], timeout=1500)
 
 
+def test_more_ranks_than_planes():
+    """ragged edge: a distributed dimension shorter than the processor grid leaves some ranks with EMPTY local blocks
+    (block distribution init.C:1834-1862 gives the first P - N%P ranks floor(N/P) = 0 planes); those ranks still take part in
+    every barrier and receive their share of the output"""
+    cs = [fwd((8, 6, 3), [1, 1, 4]), bwd((8, 6, 3), [1, 1, 4]), fwd((8, 3, 5), [1, 4, 1]), bwd((8, 3, 5), [1, 4, 1]),
+          c2c((4, 3, 3), [1, 2, 2]), c2c((5, 1, 3), [1, 2, 2])]
+    launch(4, cs)
+    launch(4, cs[:2], env_extra={"P3DFFT_B200_OVERLAP_ALIGN": "1", "P3DFFT_B200_OVERLAP_CHUNKS": "2"})
+
+
 def test_r2c_1024_with_exchange_segments():
     """pencil grid: the 1024-point R2C stage (symmetric-column last pass) is itself an exchange stage, so its out-of-order
     rows go through the per-peer segment table; also as the local stage of an overlapped pair on a slab grid"""
