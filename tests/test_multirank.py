@@ -104,6 +104,17 @@ def test_more_ranks_than_planes():
     launch(4, cs[:2], env_extra={"P3DFFT_B200_OVERLAP_ALIGN": "1", "P3DFFT_B200_OVERLAP_CHUNKS": "2"})
 
 
+def test_in_place_multirank_and_odd_grids():
+    """in == out with the overwrite flag across ranks (also with overlapped pairs, whose exchange-first form must not let the
+    local stage overwrite the exchange stage's input), and processor grids that are not powers of two"""
+    n = (16, 12, 10)
+    ip = [fwd(n, [1, 1, 2], inplace=True), bwd(n, [1, 1, 2], inplace=True), c2c(n, [1, 1, 2], inplace=True),
+          c2c(n, [1, 1, 2], inplace=True, dmap2=[0, 1, 2], mo2=[0, 1, 2], expect_pairs=False)]
+    launch(2, ip)
+    launch(2, ip, env_extra=FORCE_PAIRS)
+    launch(6, [fwd((12, 9, 10), [1, 3, 2]), bwd((12, 9, 10), [1, 3, 2]), c2c((7, 9, 10), [1, 2, 3]), fwd((12, 9, 10), [1, 2, 3], deriv=2)])
+
+
 def test_r2c_1024_with_exchange_segments():
     """pencil grid: the 1024-point R2C stage (symmetric-column last pass) is itself an exchange stage, so its out-of-order
     rows go through the per-peer segment table; also as the local stage of an overlapped pair on a slab grid"""
