@@ -192,3 +192,11 @@ def test_gpu_multirank_parity(nranks):
     launch(nranks, cs, mode="gpu", timeout=1200)
     if nranks == 4:
         launch(4, "golden", mode="gpu")
+
+
+@pytest.mark.parametrize("switch", ["P3DFFT_B200_NO_PAD", "P3DFFT_B200_NO_PIPE", "P3DFFT_B200_NO_FASTCORE", "P3DFFT_B200_FORCE_GENERIC"])
+def test_kernel_ladder_switches(switch):
+    """the A/B switches of INTEGRATION.md section 7 keep working: dense intermediates, plain pow2 kernel instead of the TMA one,
+    generic kernel instead of fastcore / of everything (run in worker processes because they are read at plan creation)"""
+    cs = [fwd((128, 64, 16), [1, 1, 2], reps=1), bwd((128, 64, 16), [1, 1, 2], reps=1), c2c((100, 30, 8), [1, 2, 1], reps=1)]
+    launch(2, cs, env_extra={switch: "1"}, timeout=1500)
