@@ -200,3 +200,10 @@ def test_kernel_ladder_switches(switch):
     generic kernel instead of fastcore / of everything (run in worker processes because they are read at plan creation)"""
     cs = [fwd((128, 64, 16), [1, 1, 2], reps=1), bwd((128, 64, 16), [1, 1, 2], reps=1), c2c((100, 30, 8), [1, 2, 1], reps=1)]
     launch(2, cs, env_extra={switch: "1"}, timeout=1500)
+
+
+def test_random_multirank_cases_fixed_seed():
+    """two batches of tools/fuzz_multirank.py (random grids / processor grids / orders / kinds / chunking) with a fixed seed"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_multirank.py"), "3", "2"], capture_output=True, text=True,
+                         timeout=1500)
+    assert out.returncode == 0 and "failures 0" in out.stdout, (out.stdout[-3000:], out.stderr[-2000:])
