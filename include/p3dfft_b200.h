@@ -111,6 +111,41 @@ int p3dfftcu_stage_exec(p3dfftcu_stage st, const void *in, void *const *dst, int
 /* same, with the number of CTAs capped at max_ctas (<= 0: no cap): lets two stages share the SMs when they overlap */
 int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
                                int max_ctas);
+/* ---- one persistent launch per stage of an overlapped pair (replaces "one launch + one peer barrier per chunk"):
+ * the stage's pencils are cut into groups -- rectangles [u0,u1) x [v0,v1) of the (u, v) pencil plane, processed in table
+ * order.  A group may wait for a flag before its pencils are loaded (its input comes from another kernel that is still
+ * running: the neighbouring stage on this GPU, or the exchange stages of the peer GPUs) and may publish a flag once all
+ * its outputs are stored (to this GPU's flag words or, over NVLink, to the peers').  Flag words hold epochs that only grow.
+ * ctl: >= 1 + ngroups zeroed 8-byte device words ([0] tile counter, [1 + g] completion count of group g); launches that
+ * share one ctl share the tiles (late-joining CTAs on another stream). */
+#define P3DFFTCU_MAXGRP 24
+typedef struct p3dfftcu_group {
+  int u0, u1, v0, v1;
+  int wait_id;   /* >= 0: flag id that every wait source must have published; < 0: no wait */
+  int signal_id; /* >= 0: flag id published to every signal target on completion; < 0: none */
+} p3dfftcu_group;
+typedef struct p3dfftcu_sync {
+  int ngroups;
+  p3dfftcu_group grp[P3DFFTCU_MAXGRP];
+  void *ctl;
+  int wait_n;                             /* wait sources: flag word (j, id) = ((uint64*)wait_base)[wait_off[j] + id] */
+  const void *wait_base;
+  int wait_off[P3DFFTCU_MAXSEG];
+  unsigned long long wait_epoch[P3DFFTCU_MAXSEG];
+  int sig_n;                              /* signal targets: flag word (j, id) = ((uint64*)sig_ptr[j])[id] */
+  void *sig_ptr[P3DFFTCU_MAXSEG];
+  unsigned long long sig_epoch[P3DFFTCU_MAXSEG];
+} p3dfftcu_sync;
+/* 1 if the kernel variant picked for this stage can run with tile groups (the TMA-fed power-of-two kernels) */
+int p3dfftcu_stage_sync_capable(p3dfftcu_stage st);
+int p3dfftcu_stage_exec_sync(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
+                             int max_ctas, const p3dfftcu_sync *sy);
+/* writes epoch[j] into word ids[i] of every flag array ptrs[j] (groups that are empty on this rank still have to be
+ * published), stream-ordered */
+int p3dfftcu_flags_publish(void *const *ptrs, const unsigned long long *epochs, int n, const int *ids, int nids, void *stream);
+/* seconds a kernel waits for a peer (barrier or flag) before it traps; 0 = for ever (default; P3DFFT_B200_PEER_TIMEOUT_S) */
+void p3dfftcu_set_peer_timeout(double seconds);
+
 /* human-readable name of the kernel variant picked for this stage */
 const char *p3dfftcu_stage_variant(p3dfftcu_stage st);
 
@@ -135,11 +170,12 @@ int p3dfftcu_event_elapsed(void *ev0, void *ev1, float *ms);
 int p3dfftcu_ipc_export(void *ptr, char handle[P3DFFTCU_IPC_BYTES]);
 int p3dfftcu_ipc_open(const char handle[P3DFFTCU_IPC_BYTES], void **ptr);
 int p3dfftcu_ipc_close(void *ptr);
-/* stream-ordered barrier among n peers (self included or not): writes `epoch` into word `my_slot` of every
- * peer_flags[j] array, then waits until words peer_slots[j] of my_flags all reach `epoch`.  Flag arrays are
- * 8-byte words, zero-initialised, one word per world rank; epochs must increase from call to call. */
+/* stream-ordered barrier among n peers (self included or not): writes epochs[j] into word `my_slot` of
+ * peer_flags[j], then waits until word peer_slots[j] of my_flags reaches epochs[j].  Flag arrays are 8-byte
+ * words, zero-initialised, one word per world rank; epochs[j] = number of barriers this rank and peer j have run
+ * together (it grows from call to call and both sides count the same calls). */
 int p3dfftcu_peer_barrier(void *const *peer_flags, const int *peer_slots, int n, void *my_flags, int my_slot,
-                          unsigned long long epoch, void *stream);
+                          const unsigned long long *epochs, void *stream);
 
 long long p3dfftcu_launch_count(void);
 

@@ -6,6 +6,7 @@
 
 #ifndef P3B_LAUNCH
 #define P3B_LAUNCH(kernel, grid, block, smem, stream, params) kernel<<<grid, block, smem, stream>>>(params)
+#define P3B_LAUNCH2(kernel, grid, block, smem, stream, p1, p2) kernel<<<grid, block, smem, stream>>>(p1, p2)
 #endif
 
 namespace p3b {
@@ -67,6 +68,36 @@ struct StageParams {
   int deriv_g;      // > 0: spectral derivative epilogue with full length g
   int nseg;
   SegDev seg[P3DFFTCU_MAXSEG];
+};
+
+// ---- tile groups and flags: one persistent launch per stage of an overlapped pair (pow2_pipe.cuh, SYNC = 1)
+// The pencils of a stage are cut into groups (rectangles of the (u, v) pencil plane, processed in table order).  A group may
+// WAIT for a flag before its pencils are loaded (its input is produced by another kernel: the neighbouring stage on this GPU,
+// or the exchange stages of the peer GPUs) and may SIGNAL a flag once all its outputs have been stored.  Flags are 8-byte
+// words holding an epoch: the number of flag-synchronised execs the writer and the reader have run TOGETHER (kept per pair
+// of ranks by the host, so plans on different sub-communicators cannot confuse each other); epochs only grow, so flags are
+// never reset.
+#define P3B_MAXGRP 24
+#define P3B_MAXSRC 32
+struct TileGroupDev {
+  int u0, u1, v0, v1;    // pencil ranges [u0,u1) x [v0,v1)
+  int tiles_u, tiles_v;  // tiles of the group along u and v
+  long long tile0;       // global number of its first tile
+  int wait_id;           // >= 0: flag id every wait source must have published before the group is loaded
+  int signal_id;         // >= 0: flag id published to every signal target when the group is complete
+};
+struct SyncDev {
+  int ngroups;
+  int dynamic;                  // tiles come from the counter ctl[0] instead of blockIdx striding (TS = 1 kernels)
+  unsigned long long *ctl;      // [0] tile counter, [1 + g] pencils of group g completed (zeroed by the host before the launch)
+  unsigned long long timeout_ns;  // > 0: trap when a wait lasts longer (0 = wait for ever)
+  const unsigned long long *wait_base;  // word of (source j, id) = wait_base[wait_off[j] + id]
+  int wait_n, sig_n;
+  int wait_off[P3B_MAXSRC];
+  unsigned long long wait_epoch[P3B_MAXSRC];  // value source j writes for this exec
+  unsigned long long *sig_ptr[P3B_MAXSRC];    // word of (target j, id) = sig_ptr[j][id] (peer memory over NVLink, or local)
+  unsigned long long sig_epoch[P3B_MAXSRC];   // value target j expects for this exec
+  TileGroupDev grp[P3B_MAXGRP];
 };
 
 // derivative multiplier of output index k for full spectral length g (reference exec.C:228-287):

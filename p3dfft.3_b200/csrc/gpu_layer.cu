@@ -199,9 +199,17 @@ template <typename T> __global__ void deriv_kernel(const __grid_constant__ Deriv
 struct BarrierParams {
   unsigned long long *peer[64];
   int slot[64];
+  unsigned long long epoch[64];
   unsigned long long *mine;
   int n, my_slot;
-  unsigned long long epoch;
+  unsigned long long timeout_ns;  // 0: wait for ever
+};
+
+struct PublishParams {
+  unsigned long long *ptr[P3B_MAXSRC];
+  unsigned long long epoch[P3B_MAXSRC];
+  int ids[P3B_MAXGRP];
+  int n, nids;
 };
 
 #ifndef P3B_EMU
@@ -210,23 +218,40 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
   if (j >= p.n) return;
   __threadfence_system();
   unsigned long long *remote = p.peer[j] + p.my_slot;
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(p.epoch) : "memory");
+  const unsigned long long epoch = p.epoch[j];
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
   const unsigned long long *mine = p.mine + p.slot[j];
   unsigned long long t0, t1, v;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-    if (v >= p.epoch) break;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 30000000000ull) {  // 30 s: a peer died; fail loudly instead of hanging the GPU
-      printf("p3dfft_b200: peer barrier timed out (slot %d waiting for slot %d, epoch %llu, seen %llu)\n", p.my_slot,
-             p.slot[j], p.epoch, v);
-      __trap();
+    if (v >= epoch) break;
+    // like MPI_Alltoallv the barrier waits for ever by default (a peer may legitimately be late: a checkpoint, a debugger,
+    // a lazy module load); P3DFFT_B200_PEER_TIMEOUT_S=<seconds> makes a dead peer fail loudly instead of hanging the GPU
+    if (p.timeout_ns) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > p.timeout_ns) {
+        printf("p3dfft_b200: peer barrier timed out (slot %d waiting for slot %d, epoch %llu, seen %llu)\n", p.my_slot, p.slot[j],
+               epoch, v);
+        __trap();
+      }
     }
     __nanosleep(200);
   }
 }
+
+__global__ void flags_publish_kernel(const __grid_constant__ PublishParams p) {
+  const int j = threadIdx.x / P3B_MAXGRP, i = threadIdx.x % P3B_MAXGRP;
+  if (j >= p.n || i >= p.nids) return;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.ptr[j] + p.ids[i]), "l"(p.epoch[j]) : "memory");
+}
 #endif
+
+unsigned long long g_peer_timeout_ns = [] {
+  const char *e = getenv("P3DFFT_B200_PEER_TIMEOUT_S");
+  const double s = e ? atof(e) : 0.0;
+  return s > 0 ? (unsigned long long)(s * 1e9) : 0ull;
+}();
 
 // ------------------------------------------------------------------ stage object
 enum Variant { V_GENERIC = 0, V_POW2 = 1, V_PIPE = 2, V_FAST = 3 };
@@ -492,6 +517,7 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   pp->ntiles = pp->tiles_u * pp->tiles_v;
   pp->vfast = d.nv > 1 && (d.nu <= 1 || d.seg[0].os_v < d.seg[0].os_u);
   if (cudaFuncSetAttribute(info->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(info->func_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, info->func, info->threads, info->smem) != cudaSuccess) return 1;
   if (occ < 1) occ = 1;
@@ -721,6 +747,95 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
   return 0;
 }
 
+// 0: no tile-group form; 1: yes, tiles by CTA striding (all CTAs must be resident); 2: yes, tiles from a counter (launches that
+// share one control block share the work)
+int p3dfftcu_stage_sync_capable(p3dfftcu_stage st) {
+  if (st->empty || st->variant != V_PIPE || st->pp.ntiles <= 0) return 0;
+  return st->pp.ld ? 2 : 1;
+}
+
+int p3dfftcu_stage_exec_sync(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
+                             int max_ctas, const p3dfftcu_sync *sy) {
+  if (!p3dfftcu_stage_sync_capable(st)) return failmsg("stage: this kernel variant has no tile-group form");
+  if (((uintptr_t)in) % 16) return failmsg("stage: the tile-group form needs a 16-byte aligned input");
+  if (deriv_g > 0 && st->d.dt_out != 2) return failmsg("stage: spectral derivative needs complex output");
+  if (sy->ngroups < 1 || sy->ngroups > P3B_MAXGRP || sy->wait_n > P3B_MAXSRC || sy->sig_n > P3B_MAXSRC)
+    return failmsg("stage: bad tile-group table");
+  StageParams P = st->P;
+  P.in = in;
+  P.deriv_g = deriv_g;
+  for (int s = 0; s < P.nseg; s++) {
+    int slot = st->d.seg[s].slot;
+    if (slot < 0 || slot >= ndst || !dst[slot]) return failmsg("stage: missing destination buffer for a segment");
+    P.seg[s].base = dst[slot];
+  }
+  const PipePlan &pp = st->pp;
+  P.tile_u = pp.tile_u; P.tile_v = pp.tile_v; P.tu_log2 = pp.tu_log2;
+  P.load_ord = pp.load_ord; P.store_ord = pp.store_ord;
+  P.tiles_u = pp.tiles_u; P.tiles_v = pp.tiles_v; P.vfast = pp.vfast;
+  SyncDev Y;
+  memset(&Y, 0, sizeof Y);
+  Y.ngroups = sy->ngroups;
+  Y.dynamic = pp.ld ? 1 : 0;  // the transposed-output kernels synchronise the CTA once per tile: tiles from a counter
+  Y.ctl = (unsigned long long *)sy->ctl;
+  Y.timeout_ns = g_peer_timeout_ns;
+  Y.wait_base = (const unsigned long long *)sy->wait_base;
+  Y.wait_n = sy->wait_n;
+  Y.sig_n = sy->sig_n;
+  for (int j = 0; j < sy->wait_n; j++) { Y.wait_off[j] = sy->wait_off[j]; Y.wait_epoch[j] = sy->wait_epoch[j]; }
+  for (int j = 0; j < sy->sig_n; j++) { Y.sig_ptr[j] = (unsigned long long *)sy->sig_ptr[j]; Y.sig_epoch[j] = sy->sig_epoch[j]; }
+  long long t0 = 0;
+  for (int g = 0; g < sy->ngroups; g++) {
+    const p3dfftcu_group &G = sy->grp[g];
+    if (G.u0 < 0 || G.v0 < 0 || G.u1 > st->d.nu || G.v1 > st->d.nv) return failmsg("stage: tile group outside the stage");
+    TileGroupDev &D = Y.grp[g];
+    D.u0 = G.u0; D.u1 = G.u1; D.v0 = G.v0; D.v1 = G.v1;
+    D.tiles_u = G.u1 > G.u0 ? (G.u1 - G.u0 + pp.tile_u - 1) / pp.tile_u : 0;
+    D.tiles_v = G.v1 > G.v0 ? (G.v1 - G.v0 + pp.tile_v - 1) / pp.tile_v : 0;
+    if (D.tiles_u == 0 || D.tiles_v == 0) D.tiles_u = D.tiles_v = 0;  // (an empty group: the host publishes its flag)
+    D.tile0 = t0;
+    D.wait_id = G.wait_id;
+    D.signal_id = G.signal_id;
+    t0 += (long long)D.tiles_u * D.tiles_v;
+  }
+  P.ntiles = t0;
+  if (t0 == 0) return 0;
+  int grid;
+  {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp.info->func_sync, pp.info->threads, pp.info->smem) != cudaSuccess || occ < 1) occ = 1;
+    grid = g_num_sms * occ;
+  }
+  if (t0 < grid) grid = (int)t0;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  pp.info->launch_sync(P, Y, grid, (cudaStream_t)stream);
+  g_launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int p3dfftcu_flags_publish(void *const *ptrs, const unsigned long long *epochs, int n, const int *ids, int nids, void *stream) {
+  if (n > P3B_MAXSRC || nids > P3B_MAXGRP) return failmsg("flags publish: too many targets");
+  if (n <= 0 || nids <= 0) return 0;
+#ifndef P3B_EMU
+  PublishParams p;
+  memset(&p, 0, sizeof p);
+  for (int j = 0; j < n; j++) { p.ptr[j] = (unsigned long long *)ptrs[j]; p.epoch[j] = epochs[j]; }
+  for (int i = 0; i < nids; i++) p.ids[i] = ids[i];
+  p.n = n; p.nids = nids;
+  flags_publish_kernel<<<1, P3B_MAXSRC * P3B_MAXGRP, 0, (cudaStream_t)stream>>>(p);
+  g_launches++;
+  CK(cudaGetLastError());
+#else
+  (void)stream;
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < nids; i++) __atomic_store_n((unsigned long long *)ptrs[j] + ids[i], epochs[j], __ATOMIC_RELEASE);
+#endif
+  return 0;
+}
+
+void p3dfftcu_set_peer_timeout(double seconds) { g_peer_timeout_ns = seconds > 0 ? (unsigned long long)(seconds * 1e9) : 0ull; }
+
 int p3dfftcu_deriv(const void *in, void *out, int prec, const int sd[3], int ldir, int g, int gstart, void *stream) {
   long long total = (long long)sd[0] * sd[1] * sd[2];
   if (total == 0) return 0;
@@ -794,18 +909,19 @@ int p3dfftcu_ipc_close(void *ptr) {
 }
 
 int p3dfftcu_peer_barrier(void *const *peer_flags, const int *peer_slots, int n, void *my_flags, int my_slot,
-                          unsigned long long epoch, void *stream) {
+                          const unsigned long long *epochs, void *stream) {
   if (n > 64) return failmsg("peer barrier: too many peers");
   BarrierParams p;
   memset(&p, 0, sizeof p);
   for (int j = 0; j < n; j++) {
     p.peer[j] = (unsigned long long *)peer_flags[j];
     p.slot[j] = peer_slots[j];
+    p.epoch[j] = epochs[j];
   }
   p.mine = (unsigned long long *)my_flags;
   p.n = n;
   p.my_slot = my_slot;
-  p.epoch = epoch;
+  p.timeout_ns = g_peer_timeout_ns;
 #ifndef P3B_EMU
   peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(p);
   g_launches++;
@@ -814,15 +930,19 @@ int p3dfftcu_peer_barrier(void *const *peer_flags, const int *peer_slots, int n,
 #else
   // CPU emulation: same protocol with host atomics on the shared-memory "device" buffers
   (void)stream;
-  for (int j = 0; j < n; j++) __atomic_store_n(p.peer[j] + p.my_slot, p.epoch, __ATOMIC_RELEASE);
+  for (int j = 0; j < n; j++) __atomic_store_n(p.peer[j] + p.my_slot, p.epoch[j], __ATOMIC_RELEASE);
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int j = 0; j < n; j++) {
     long spins = 0;
-    while (__atomic_load_n(p.mine + p.slot[j], __ATOMIC_ACQUIRE) < p.epoch) {
+    while (__atomic_load_n(p.mine + p.slot[j], __ATOMIC_ACQUIRE) < p.epoch[j]) {
       if (++spins > 2000) {
-        struct timespec ts = {0, 100000};
+        struct timespec ts = {0, 100000}, t1;
         nanosleep(&ts, nullptr);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double el = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+        if (p.timeout_ns && el * 1e9 > (double)p.timeout_ns) return failmsg("peer barrier timed out (emulation)");
       }
-      if (spins > 600000) return failmsg("peer barrier timed out (emulation)");
     }
   }
   return 0;

@@ -71,6 +71,80 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void group_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif
 
+// ------------------------------------------------------------------ flags between kernels (SYNC = 1 variants)
+#ifdef P3B_EMU
+inline unsigned long long flag_ld(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void flag_st(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long ctr_add(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+inline void fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void fence_proxy_async_all() {}
+inline unsigned long long now_ns() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+inline void spin_pause() {
+  struct timespec ts = {0, 20000};
+  nanosleep(&ts, nullptr);
+}
+inline void sync_trap(const char *what) {
+  fprintf(stderr, "p3dfft_b200 (emulation): %s\n", what);
+  abort();
+}
+#else
+__device__ __forceinline__ unsigned long long flag_ld(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void flag_st(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ctr_add(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+__device__ __forceinline__ void fence_sys() { __threadfence_system(); }
+// data written through the generic proxy (by other SMs or other GPUs) is about to be read by bulk copies (async proxy)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void spin_pause() { __nanosleep(100); }
+__device__ __forceinline__ void sync_trap(const char *what) {
+  printf("p3dfft_b200: %s\n", what);
+  __trap();
+}
+#endif
+
+// have all wait sources published flag `id` for this exec?  blocking: spin until they have (trap after Y.timeout_ns if set)
+__device__ __forceinline__ bool flags_ready(const SyncDev &Y, int id, bool blocking) {
+  for (int j = 0; j < Y.wait_n; j++) {
+    const unsigned long long *w = Y.wait_base + Y.wait_off[j] + id;
+    const unsigned long long want = Y.wait_epoch[j];
+    if (flag_ld(w) >= want) continue;
+    if (!blocking) return false;
+    const unsigned long long t0 = now_ns();
+    while (flag_ld(w) < want) {
+      spin_pause();
+      if (Y.timeout_ns && now_ns() - t0 > Y.timeout_ns) sync_trap("timed out waiting for a tile-group flag (a peer rank died or never ran this exec)");
+    }
+  }
+  fence_proxy_async_all();
+  return true;
+}
+
+// `add` pencils of group g are complete (the caller has synchronised the threads that stored them): count them, and publish
+// the group's flag to every target when it was the last contribution
+__device__ __forceinline__ void group_done(const SyncDev &Y, int g, unsigned long long add, unsigned long long total) {
+  fence_sys();
+  const unsigned long long prev = ctr_add(Y.ctl + 1 + g, add);
+  if (prev + add == total) {
+    fence_sys();
+    const int id = Y.grp[g].signal_id;
+    for (int j = 0; j < Y.sig_n; j++) flag_st(Y.sig_ptr[j] + id, Y.sig_epoch[j]);
+  }
+}
+
 // store of data that is not read again before it leaves the L2 (every stage output is >> the 126 MB L2).
 // -DP3B_STREAM_STORES selects st.global.cs (evict-first); measured on the 1024^3 round trip it makes no difference
 // (18.38 / 18.33 ms against 18.43 / 18.14 ms, alternating runs on one box), so the default stays a plain store
@@ -96,7 +170,7 @@ template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
   // the banks; XP0 = M + M/16 + 1 is odd
   enum { PITCH = sizeof(T) == 8 ? XP0 : ((XP0 + 1) % 4 == 2 ? XP0 + 1 : XP0 + 3) };
   enum { T2N = R1 * R2, T3N = R3 > 1 ? R3 * TP : 0 };
-  static constexpr size_t bar_bytes = 128;
+  static constexpr size_t bar_bytes = 256;  // P mbarriers (<= 128 bytes), then two words for the tile numbers handed out dynamically
   static constexpr size_t smem = bar_bytes + ((size_t)P * PITCH + T2N + T3N) * csz;
   static constexpr bool valid = (THREADS >= 32) && (THREADS <= 1024) && (P <= 16) && (smem <= kPipeSmemMax) && (TS ? P >= 2 : true) &&
                                 (TP > 32 ? P <= 15 : true);
@@ -204,9 +278,9 @@ template <typename T, typename C> __device__ __forceinline__ C r2c_split(C zk, C
 }
 
 // ------------------------------------------------------------------ the kernel
-template <typename T, int M, int KIND, int P, int TS>
-__global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, TS>::THREADS, PipeCfg<T, M, KIND, P, TS>::MINB)
-pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
+// SY = 1: tile groups with wait / signal flags (SyncDev, common.cuh) -- the persistent kernels of an overlapped pair
+template <typename T, int M, int KIND, int P, int TS, int SY>
+__device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncDev *Yp) {
   typedef typename cx<T>::type C;
   typedef PipeCfg<T, M, KIND, P, TS> Cfg;
   constexpr int E = Cfg::E, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
@@ -223,6 +297,7 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   constexpr bool r2c_sym = r2c && E == 16 && (R3 == 2 || R3 == 4 || R3 == 8);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);  // one mbarrier per pencil: "landed"
+  long long *snext = reinterpret_cast<long long *>(smem_raw + 128);               // SY: tile numbers from the dynamic counter
   C *B = reinterpret_cast<C *>(smem_raw + Cfg::bar_bytes);
   C *T2 = B + P * PITCH;   // [R2][R1]
   C *T3 = T2 + Cfg::T2N;   // [R3][TP]
@@ -253,18 +328,45 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   // consecutive tile numbers (= concurrently running CTAs) run along the dimension that is closer to unit stride in the
   // OUTPUT, so that the stores of neighbouring CTAs fill whole DRAM pages together
   const bool vfast = Q.vfast != 0;
-  auto tile_origin = [&](long long tl, long long &u0, long long &v0) {
-    const long long iu = vfast ? tl / Q.tiles_v : tl % Q.tiles_u, iv = vfast ? tl % Q.tiles_v : tl / Q.tiles_u;
-    u0 = iu * tile_u;
-    v0 = iv * Q.tile_v;
+  // SY: the tiles are numbered group by group (TileGroupDev); g = group of tile tl
+  auto tile_origin = [&](long long tl, int g, long long &u0, long long &v0) {
+    if constexpr (SY) {
+      const TileGroupDev &G = Yp->grp[g];
+      const long long l = tl - G.tile0;
+      const long long iu = vfast ? l / G.tiles_v : l % G.tiles_u, iv = vfast ? l % G.tiles_v : l / G.tiles_u;
+      u0 = G.u0 + iu * tile_u;
+      v0 = G.v0 + iv * Q.tile_v;
+    } else {
+      const long long iu = vfast ? tl / Q.tiles_v : tl % Q.tiles_u, iv = vfast ? tl % Q.tiles_v : tl / Q.tiles_u;
+      u0 = iu * tile_u;
+      v0 = iv * Q.tile_v;
+    }
   };
-  auto issue = [&](long long tl) {
+  auto group_of = [&](long long tl, int g) {
+    if constexpr (SY)
+      while (g + 1 < Yp->ngroups && tl >= Yp->grp[g + 1].tile0) g++;
+    return g;
+  };
+  int gI = 0, gReady = -1;  // leaders: group of the tile being issued; groups <= gReady have had their flag seen
+  long long pend = -1;      // leaders: tile whose load waits for its group's flag (issued, blocking, at the top of the loop)
+  auto issue = [&](long long tl, bool blocking) {
     if (tA == 0 && tl < Q.ntiles) {
+      if constexpr (SY) {
+        gI = group_of(tl, gI);
+        if (gI > gReady) {
+          const int wid = Yp->grp[gI].wait_id;
+          if (wid >= 0 && !flags_ready(*Yp, wid, blocking)) {
+            pend = tl;
+            return;
+          }
+          gReady = gI;
+        }
+      }
       long long u, v;
-      tile_origin(tl, u, v);
+      tile_origin(tl, gI, u, v);
       u += puA;
       v += pvA;
-      const bool live = u < Q.nu && v < Q.nv;
+      const bool live = SY ? (u < Yp->grp[gI].u1 && v < Yp->grp[gI].v1) : (u < Q.nu && v < Q.nv);
       fence_async_smem();
       mbar_expect_tx(bar, live ? bytes : 0u);
       if (live) {
@@ -282,17 +384,35 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
   if constexpr (c2r) wt = tw[tA];
 
   if (tid < P) mbar_init(bars + tid, 1);
+  bool dynamic = false;
+  if constexpr (SY && TS) dynamic = Yp->dynamic != 0;
+  if constexpr (SY)
+    if (dynamic && tid == 0) snext[0] = (long long)ctr_add(Yp->ctl, 1ull);
   __syncthreads();
 
   long long tile = blockIdx.x;
+  if constexpr (SY)
+    if (dynamic) tile = snext[0];
   unsigned parity = 0;
-  issue(tile);
-  for (; tile < Q.ntiles; tile += gridDim.x) {
+  int gS = 0, it = 0;            // SY: group of the tile being processed; iteration count
+  unsigned long long cnt = 0;    // SY: pencils of group gS this thread has to account for
+  issue(tile, true);
+  while (tile < Q.ntiles) {
+    long long nxt = tile + gridDim.x;
+    if constexpr (SY) {
+      gS = group_of(tile, gS);
+      if (dynamic && tid == 0) snext[(it + 1) & 1] = (long long)ctr_add(Yp->ctl, 1ull);  // read after the next CTA barrier
+      if (tA == 0 && pend >= 0) {  // the prefetch found the group's flag not yet set: wait for it now
+        const long long t = pend;
+        pend = -1;
+        issue(t, true);
+      }
+    }
     long long uo, vo;
-    tile_origin(tile, uo, vo);
+    tile_origin(tile, gS, uo, vo);
     uo += puB;
     vo += pvB;
-    const bool live = uo < Q.nu && vo < Q.nv;
+    const bool live = SY ? (uo < Yp->grp[gS].u1 && vo < Yp->grp[gS].v1) : (uo < Q.nu && vo < Q.nv);
     C v[E];
     mbar_wait(bar, parity);  // this thread's pencil (mapping A) has landed
     parity ^= 1;
@@ -346,7 +466,8 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         }
       }
       syncB();  // every value is in registers: the buffers are free for the next tile
-      issue(tile + gridDim.x);
+      if constexpr (SY) if (dynamic) nxt = snext[(it + 1) & 1];
+      issue(nxt, false);
       C w3[R3];  // w_M^{q t}
 #pragma unroll
       for (int q = 1; q < R3; q++) w3[q] = T3[q * TP + tB];
@@ -404,7 +525,8 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
     smem_gather<T, M, E>(v, BB, tB);  // re-maps to the store side when TS
     if constexpr (!r2c) {
       syncB();  // every value is back in registers: the buffers are free for the next tile
-      issue(tile + gridDim.x);
+      if constexpr (SY) if (dynamic) nxt = snext[(it + 1) & 1];
+      issue(nxt, false);
     }
     if constexpr (R3 > 1) reg_pass3<T, M, E, R3>(v, tB, T3);
     else reg_pass2<T, M, E, R1, R2>(v, tB, T2);
@@ -434,7 +556,8 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         if (m == 0) xM = mk<T>(zk.x - zk.y, (T)0);  // X[M], used by the thread that owns k = 0
       }
       syncB();
-      issue(tile + gridDim.x);
+      if constexpr (SY) if (dynamic) nxt = snext[(it + 1) & 1];
+      issue(nxt, false);
       if (live) {
         if (Q.nseg == 1 && Q.deriv_g <= 0) {  // local stage: one base pointer, constant stride between a thread's stores
           const SegDev &sg = Q.seg[0];
@@ -478,13 +601,51 @@ pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
         for (int m = 0; m < E; m++) store_out<T>(Q, tB + m * TP, uo, vo, bwd ? cconj(v[m]) : v[m]);
       }
     }
+    if constexpr (SY) {
+      // a group that signals: count this tile's pencils; when the CTA (TS) or the pencil's thread group (!TS) leaves the
+      // group, add them to the group's counter -- whoever completes it publishes the flag
+      if (Yp->grp[gS].signal_id >= 0) {
+        const bool leaving = nxt >= Q.ntiles || group_of(nxt, gS) != gS;
+        const unsigned long long total = (unsigned long long)Yp->grp[gS].tiles_u * Yp->grp[gS].tiles_v * P;
+        if (TS) {
+          cnt += P;
+          if (leaving) {
+            __syncthreads();
+            if (tid == 0) group_done(*Yp, gS, cnt, total);
+            cnt = 0;
+          }
+        } else {
+          cnt += 1;
+          if (leaving) {
+            syncA();
+            if (tA == 0) group_done(*Yp, gS, cnt, total);
+            cnt = 0;
+          }
+        }
+      }
+      it++;
+    }
+    tile = nxt;
   }
+}
+
+template <typename T, int M, int KIND, int P, int TS>
+__global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, TS>::THREADS, PipeCfg<T, M, KIND, P, TS>::MINB)
+pow2_pipe_kernel(const __grid_constant__ StageParams Q) {
+  pow2_pipe_body<T, M, KIND, P, TS, 0>(Q, nullptr);
+}
+
+template <typename T, int M, int KIND, int P, int TS>
+__global__ void __launch_bounds__(PipeCfg<T, M, KIND, P, TS>::THREADS, PipeCfg<T, M, KIND, P, TS>::MINB)
+pow2_pipe_sync_kernel(const __grid_constant__ StageParams Q, const __grid_constant__ SyncDev Y) {
+  pow2_pipe_body<T, M, KIND, P, TS, 1>(Q, &Y);
 }
 
 // ------------------------------------------------------------------ host side: lookup tables, one per (T, KIND, TS)
 struct PipeInfo {
   void (*launch)(const StageParams &, int grid, cudaStream_t);
-  const void *func;
+  void (*launch_sync)(const StageParams &, const SyncDev &, int grid, cudaStream_t);
+  const void *func, *func_sync;
   int threads, ts, minb;
   size_t smem;
 };
@@ -494,13 +655,19 @@ template <typename T, int M, int KIND, int P, int TS> void pipe_launcher(const S
   P3B_LAUNCH((pow2_pipe_kernel<T, M, KIND, P, TS>), grid, Cfg::THREADS, Cfg::smem, s, Q);
 }
 
+template <typename T, int M, int KIND, int P, int TS> void pipe_sync_launcher(const StageParams &Q, const SyncDev &Y, int grid, cudaStream_t s) {
+  typedef PipeCfg<T, M, KIND, P, TS> Cfg;
+  P3B_LAUNCH2((pow2_pipe_sync_kernel<T, M, KIND, P, TS>), grid, Cfg::THREADS, Cfg::smem, s, Q, Y);
+}
+
 template <typename T, int M, int KIND, int P, int TS> const PipeInfo *pipe_info_one() {
   typedef PipeCfg<T, M, KIND, P, TS> Cfg;
   if constexpr (!Cfg::valid) {
     return nullptr;
   } else {
-    static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, Cfg::THREADS,
-                                  TS, Cfg::MINB, Cfg::smem};
+    static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, pipe_sync_launcher<T, M, KIND, P, TS>,
+                                  (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, (const void *)pow2_pipe_sync_kernel<T, M, KIND, P, TS>,
+                                  Cfg::THREADS, TS, Cfg::MINB, Cfg::smem};
     return &info;
   }
 }

@@ -1,5 +1,6 @@
 // pow2_pipe_inst.cu -- instantiates the pipelined stage kernels of ONE (precision, kind) pair; the Makefile compiles this
 // file eight times (-DPIPE_PREC=4|8 -DPIPE_KIND=1..4) so the instantiations build in parallel.
+#define P3B_PIPE_TU 1
 #include "pow2_pipe.cuh"
 
 #if PIPE_PREC == 8

@@ -368,6 +368,7 @@ inline bool pow2_supported(const p3dfftcu_stage_desc &d) {
   return M == 64 || M == 128 || M == 256 || M == 512 || M == 1024 || M == 2048 || M == 4096;
 }
 
+#ifndef P3B_PIPE_TU  // (the pow2_pipe_inst.cu units only need the device code above: skip ~100 kernel instantiations each)
 template <typename T, int M, int THREADS> void pow2_launcher(const StageParams &P, int grid, int threads, size_t smem, cudaStream_t s) {
   (void)threads;
   P3B_LAUNCH((pow2_stage_kernel<T, M, THREADS, Pow2MinBlocks<T, THREADS>::VALUE>), grid, THREADS, smem, s, P);
@@ -490,5 +491,6 @@ inline int pow2_launch(const Pow2Plan &pl, StageParams P, cudaStream_t s) {
   pl.launch(P, pl.grid, pl.threads, pl.smem, s);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
+#endif  // P3B_PIPE_TU
 
 }  // namespace p3b

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 
 #include "plan.h"
 
@@ -32,109 +33,193 @@ static void fatal(const Plan *pl, const char *what) {
 static Workspace g_ws;
 Workspace &workspace() { return g_ws; }
 
-static void close_peers(Workspace &ws, int rank) {
-  for (int w = 0; w < 2; w++) {
-    for (size_t r = 0; r < ws.peer_buf[w].size(); r++)
-      if ((int)r != rank && ws.peer_buf[w][r]) p3dfftcu_ipc_close(ws.peer_buf[w][r]);
-    ws.peer_buf[w].clear();
+static bool ws_init(Workspace &ws, std::string *err) {
+  if (ws.world_size) return true;
+  int flag = 0;
+  MPI_Initialized(&flag);
+  ws.world_rank = 0;
+  ws.world_size = 1;
+  if (flag) {
+    MPI_Comm_rank(MPI_COMM_WORLD, &ws.world_rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &ws.world_size);
   }
-}
-
-bool workspace_reserve(long long bytes, MPI_Comm comm, int nranks, int rank, std::string *err) {
-  Workspace &ws = g_ws;
-  // agree on whether (and to what size) to grow: every rank ends up with the same capacity
-  long long want = bytes > ws.bytes ? bytes : ws.bytes, wmax = want;
-  long long have = (ws.nranks == nranks) ? ws.bytes : 0, hmin = have;
-  MPI_Allreduce(&want, &wmax, 1, MPI_LONG_LONG, MPI_MAX, comm);
-  MPI_Allreduce(&have, &hmin, 1, MPI_LONG_LONG, MPI_MIN, comm);
-  if (hmin >= wmax && ws.buf[0]) return true;
-  if (p3dfftcu_stream_sync(current_stream())) {
-    *err = p3dfftcu_last_error();
+  if (ws.world_size > WS_MAX_RANKS) {
+    *err = "more than 64 ranks: the peer flag arrays of this build hold 64 slots";
+    ws.world_size = 0;
     return false;
   }
-  close_peers(ws, rank);
+  ws.peers.assign(ws.world_size, PeerMap());
+  ws.epoch_with.assign(ws.world_size, 0);
+  return true;
+}
+
+static void close_peer(Workspace &ws, int wr, bool flags_too) {
+  PeerMap &pm = ws.peers[wr];
+  if (wr != ws.world_rank) {
+    for (int w = 0; w < 2; w++)
+      if (pm.buf[w]) p3dfftcu_ipc_close(pm.buf[w]);
+    if (flags_too && pm.flags) p3dfftcu_ipc_close(pm.flags);
+  }
+  pm.buf[0] = pm.buf[1] = nullptr;
+  pm.gen = 0;
+  if (flags_too) pm.flags = nullptr;
+}
+
+// all ranks of comm agree: true only if `ok` holds everywhere (keeps the failure paths collective)
+static bool all_ok(bool ok, MPI_Comm comm) {
+  int l = ok ? 1 : 0, g = l;
+  MPI_Allreduce(&l, &g, 1, MPI_INT, MPI_MIN, comm);
+  return g != 0;
+}
+
+bool workspace_reserve(long long bytes, MPI_Comm comm, int nranks, int rank, std::string *err, std::vector<int> *world_of) {
+  Workspace &ws = g_ws;
+  bool ok = ws_init(ws, err);
+  if (!all_ok(ok, comm)) {
+    if (ok) *err = "workspace initialisation failed on another rank";
+    return false;
+  }
+  // who is who: rank in comm -> rank in MPI_COMM_WORLD
+  std::vector<int> wof(nranks, 0);
+  MPI_Allgather(&ws.world_rank, 1, MPI_INT, wof.data(), 1, MPI_INT, comm);
+  if (world_of) *world_of = wof;
+  // agree on the capacity: every rank of comm ends up with at least the largest request
+  long long want = bytes > ws.bytes ? bytes : ws.bytes, wmax = want;
+  MPI_Allreduce(&want, &wmax, 1, MPI_LONG_LONG, MPI_MAX, comm);
+  const bool grow = ws.bytes < wmax || !ws.buf[0];
+  if (grow) {
+    ok = p3dfftcu_stream_sync(current_stream()) == 0;
+    if (!ok) *err = p3dfftcu_last_error();
+  }
+  // the members that are about to re-allocate: everybody drops the mappings of their old buffers first
+  std::vector<int> grows(nranks, 0);
+  int g = grow ? 1 : 0;
+  MPI_Allgather(&g, 1, MPI_INT, grows.data(), 1, MPI_INT, comm);
+  for (int r = 0; r < nranks; r++)
+    if (grows[r] && wof[r] != ws.world_rank && ws.peers[wof[r]].gen) close_peer(ws, wof[r], false);
   MPI_Barrier(comm);
-  for (int w = 0; w < 2; w++) {
-    if (ws.buf[w]) p3dfftcu_free(ws.buf[w]);
-    ws.buf[w] = nullptr;
-    if (p3dfftcu_malloc(&ws.buf[w], (size_t)wmax)) {
-      *err = std::string("workspace allocation failed: ") + p3dfftcu_last_error();
-      return false;
+  if (grow && ok) {
+    for (int w = 0; w < 2; w++) {
+      if (ws.buf[w]) {
+        // a rank outside comm may still have the old buffer mapped: keep it until cleanup unless the whole world is here
+        if (nranks == ws.world_size) p3dfftcu_free(ws.buf[w]);
+        else ws.retired.push_back(ws.buf[w]);
+      }
+      ws.buf[w] = nullptr;
+      if (ok && p3dfftcu_malloc(&ws.buf[w], (size_t)wmax)) {
+        *err = std::string("workspace allocation failed: ") + p3dfftcu_last_error();
+        ok = false;
+      }
+    }
+    if (ok) {
+      ws.bytes = wmax;
+      ws.gen++;
+      ws.peers[ws.world_rank].buf[0] = ws.buf[0];
+      ws.peers[ws.world_rank].buf[1] = ws.buf[1];
+      ws.peers[ws.world_rank].gen = ws.gen;
+    } else ws.bytes = 0;
+  }
+  if (ok && !ws.flags) {
+    if (p3dfftcu_malloc(&ws.flags, 8 * WS_FLAG_WORDS) || p3dfftcu_memset(ws.flags, 0, 8 * WS_FLAG_WORDS, current_stream()) ||
+        p3dfftcu_stream_sync(current_stream())) {
+      *err = p3dfftcu_last_error();
+      ok = false;
+    } else ws.peers[ws.world_rank].flags = ws.flags;
+  }
+  if (nranks > 1) {
+    // exchange generation + IPC handles [buf0, buf1, flags]; a failed rank still takes part, then everybody fails together
+    const size_t rec = 16 + 3 * P3DFFTCU_IPC_BYTES;
+    std::vector<char> mine(rec, 0), all((size_t)nranks * rec);
+    unsigned long long gen = ok ? ws.gen : 0;
+    memcpy(&mine[0], &gen, 8);
+    if (ok && (p3dfftcu_ipc_export(ws.buf[0], &mine[16]) || p3dfftcu_ipc_export(ws.buf[1], &mine[16 + P3DFFTCU_IPC_BYTES]) ||
+               p3dfftcu_ipc_export(ws.flags, &mine[16 + 2 * P3DFFTCU_IPC_BYTES]))) {
+      *err = std::string("CUDA IPC export failed: ") + p3dfftcu_last_error();
+      ok = false;
+      gen = 0;
+      memcpy(&mine[0], &gen, 8);
+    }
+    MPI_Allgather(mine.data(), (int)rec, MPI_BYTE, all.data(), (int)rec, MPI_BYTE, comm);
+    for (int r = 0; r < nranks; r++) {
+      const char *h = &all[(size_t)r * rec];
+      unsigned long long pgen;
+      memcpy(&pgen, h, 8);
+      if (pgen == 0) ok = false;  // that rank failed
+      const int wr = wof[r];
+      if (!ok || wr == ws.world_rank) continue;
+      PeerMap &pm = ws.peers[wr];
+      if (pm.gen == pgen) continue;
+      if (pm.gen) close_peer(ws, wr, false);
+      if (p3dfftcu_ipc_open(h + 16, &pm.buf[0]) || p3dfftcu_ipc_open(h + 16 + P3DFFTCU_IPC_BYTES, &pm.buf[1]) ||
+          (!pm.flags && p3dfftcu_ipc_open(h + 16 + 2 * P3DFFTCU_IPC_BYTES, &pm.flags))) {
+        *err = std::string("CUDA IPC open failed (peer access between the GPUs is required): ") + p3dfftcu_last_error();
+        ok = false;
+      } else pm.gen = pgen;
     }
   }
-  ws.bytes = wmax;
-  ws.nranks = nranks;
-  if (nranks > 1) {
-    if (!ws.flags) {
-      if (p3dfftcu_malloc(&ws.flags, 8 * 64) || p3dfftcu_memset(ws.flags, 0, 8 * 64, current_stream()) ||
-          p3dfftcu_stream_sync(current_stream())) {
-        *err = p3dfftcu_last_error();
-        return false;
-      }
-    }
-    // exchange IPC handles: [buf0, buf1, flags] per rank
-    std::vector<char> mine(3 * P3DFFTCU_IPC_BYTES), all((size_t)nranks * 3 * P3DFFTCU_IPC_BYTES);
-    if (p3dfftcu_ipc_export(ws.buf[0], &mine[0]) || p3dfftcu_ipc_export(ws.buf[1], &mine[P3DFFTCU_IPC_BYTES]) ||
-        p3dfftcu_ipc_export(ws.flags, &mine[2 * P3DFFTCU_IPC_BYTES])) {
-      *err = std::string("CUDA IPC export failed: ") + p3dfftcu_last_error();
-      return false;
-    }
-    MPI_Allgather(mine.data(), 3 * P3DFFTCU_IPC_BYTES, MPI_BYTE, all.data(), 3 * P3DFFTCU_IPC_BYTES, MPI_BYTE, comm);
-    bool first_flags = ws.peer_flags.empty();
-    if (first_flags) ws.peer_flags.assign(nranks, nullptr);
-    for (int w = 0; w < 2; w++) ws.peer_buf[w].assign(nranks, nullptr);
-    for (int r = 0; r < nranks; r++) {
-      const char *h = &all[(size_t)r * 3 * P3DFFTCU_IPC_BYTES];
-      if (r == rank) {
-        ws.peer_buf[0][r] = ws.buf[0];
-        ws.peer_buf[1][r] = ws.buf[1];
-        ws.peer_flags[r] = ws.flags;
-        continue;
-      }
-      if (p3dfftcu_ipc_open(h, &ws.peer_buf[0][r]) || p3dfftcu_ipc_open(h + P3DFFTCU_IPC_BYTES, &ws.peer_buf[1][r]) ||
-          (first_flags && p3dfftcu_ipc_open(h + 2 * P3DFFTCU_IPC_BYTES, &ws.peer_flags[r]))) {
-        *err = std::string("CUDA IPC open failed (peer access between the GPUs is required): ") + p3dfftcu_last_error();
-        return false;
-      }
-    }
-    MPI_Barrier(comm);
+  if (!all_ok(ok, comm)) {
+    if (ok) *err = "workspace setup failed on another rank";
+    return false;
   }
   return true;
 }
 
+static void *g_bounce = nullptr;
+static long long g_bounce_bytes = 0;
+void *workspace_bounce(long long bytes) {
+  if (g_bounce_bytes < bytes) {
+    p3dfftcu_stream_sync(current_stream());
+    if (g_bounce) p3dfftcu_free(g_bounce);
+    g_bounce = nullptr;
+    g_bounce_bytes = 0;
+    if (p3dfftcu_malloc(&g_bounce, (size_t)bytes)) return nullptr;
+    g_bounce_bytes = bytes;
+  }
+  return g_bounce;
+}
+
 void workspace_release() {
   Workspace &ws = g_ws;
+  if (g_bounce) p3dfftcu_free(g_bounce);
+  g_bounce = nullptr;
+  g_bounce_bytes = 0;
   if (!ws.buf[0] && !ws.flags) return;
   p3dfftcu_stream_sync(current_stream());
-  int rank = 0, flag = 0;
+  int flag = 0;
   MPI_Initialized(&flag);
-  if (flag) MPI_Comm_rank(MPI_COMM_WORLD, &rank);
-  close_peers(ws, rank);
-  for (size_t r = 0; r < ws.peer_flags.size(); r++)
-    if ((int)r != rank && ws.peer_flags[r]) p3dfftcu_ipc_close(ws.peer_flags[r]);
-  ws.peer_flags.clear();
-  if (ws.nranks > 1 && flag) MPI_Barrier(MPI_COMM_WORLD);
+  for (int r = 0; r < (int)ws.peers.size(); r++) close_peer(ws, r, true);
+  if (ws.world_size > 1 && flag) MPI_Barrier(MPI_COMM_WORLD);
   for (int w = 0; w < 2; w++) {
     if (ws.buf[w]) p3dfftcu_free(ws.buf[w]);
     ws.buf[w] = nullptr;
   }
+  for (size_t i = 0; i < ws.retired.size(); i++) p3dfftcu_free(ws.retired[i]);
+  ws.retired.clear();
   if (ws.flags) p3dfftcu_free(ws.flags);
   ws.flags = nullptr;
   ws.bytes = 0;
-  ws.nranks = 0;
+  ws.gen = 0;
+  ws.world_size = 0;
+  ws.peers.clear();
+  ws.epoch_with.clear();
 }
+
+// world rank of the q-th peer of an exchange stage
+static inline int peer_wr(const Plan *pl, const StagePlan &st, size_t q) { return pl->world_of[st.peers[q].peer_world]; }
 
 static void peer_barrier(Plan *pl, const StagePlan &st, void *stream) {
   Workspace &ws = g_ws;
   int n = (int)st.peers.size();
-  void *pf[64];
-  int slots[64];
+  void *pf[WS_MAX_RANKS];
+  int slots[WS_MAX_RANKS];
+  unsigned long long ep[WS_MAX_RANKS];
   for (int q = 0; q < n; q++) {
-    pf[q] = ws.peer_flags[st.peers[q].peer_world];
-    slots[q] = st.peers[q].peer_world;
+    const int wr = peer_wr(pl, st, q);
+    pf[q] = (char *)ws.peers[wr].flags + 8 * WS_FLAG_BARRIER0;
+    slots[q] = wr;
+    ep[q] = ++ws.epoch_with[wr];
   }
-  ws.epoch++;
-  GPU(p3dfftcu_peer_barrier(pf, slots, n, ws.flags, pl->rank, ws.epoch, stream), pl, "peer barrier");
+  GPU(p3dfftcu_peer_barrier(pf, slots, n, ws.flags, ws.world_rank, ep, stream), pl, "peer barrier");
 }
 
 // CTA budgets of an overlapped pair: the exchange stage is NVLink-bound (SM-issued peer stores top out at 717 GB/s per GPU
@@ -166,7 +251,7 @@ static void run_pair(Plan *pl, size_t s, const void *ssrc, void *ldst, const int
   const int w = (int)(xs & 1);
   const int gL = deriv_g[l_first ? 0 : 1], gX = deriv_g[l_first ? 1 : 0];
   void *xdsts[P3DFFTCU_MAXSEG];
-  for (size_t q = 0; q < X.peers.size(); q++) xdsts[q] = ws.peer_buf[w][X.peers[q].peer_world];
+  for (size_t q = 0; q < X.peers.size(); q++) xdsts[q] = ws.peers[peer_wr(pl, X, q)].buf[w];
   void *xstream = pl->xstream;
   std::vector<void *> &ev = pl->sync_events;  // [0] fork, [1] join, [2 + c] chunk c of the first stage is complete
   // P3DFFT_B200_OVERLAP_TRACE=1: start/end events of every chunk on its stream, printed (rank 0) relative to the fork
@@ -245,6 +330,115 @@ static void run_pair(Plan *pl, size_t s, const void *ssrc, void *ldst, const int
       fprintf(stderr, "  end %.2f\n", te);
     }
   }
+}
+
+// The same pair as ONE persistent launch per stage: the chunks are tile groups of the two kernels, which run side by side on
+// disjoint sets of SMs; "chunk c is complete" travels as a flag word written from inside the producing kernel (to this
+// GPU's flag array when the local stage feeds the exchange stage, to every peer's over NVLink when the exchange stage
+// feeds the peers' local stages) and is awaited by the thread that issues the consuming kernel's bulk loads.  No launch and
+// no barrier kernel per chunk; the CTAs freed by the exchange kernel join the local stage's tile pool.
+static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, const int deriv_g[2], void *stream) {
+  Workspace &ws = g_ws;
+  StagePlan &first = pl->stages[s], &second = pl->stages[s + 1];
+  const bool l_first = first.pair == StagePlan::PAIR_L_THEN_X;
+  StagePlan &L = l_first ? first : second, &X = l_first ? second : first;
+  const size_t xs = l_first ? s + 1 : s;
+  const int w = (int)(xs & 1);
+  const int gL = deriv_g[l_first ? 0 : 1], gX = deriv_g[l_first ? 1 : 0];
+  const int np = (int)X.peers.size();
+  void *xdsts[P3DFFTCU_MAXSEG];
+  for (int q = 0; q < np; q++) xdsts[q] = ws.peers[peer_wr(pl, X, q)].buf[w];
+  void *xstream = pl->xstream;
+  std::vector<void *> &ev = pl->sync_events;
+  const size_t C = X.chunk_range.size();
+  int xcap, lcap;
+  pair_caps(np, &xcap, &lcap);
+  if (((uintptr_t)ssrc) % 16) {
+    // bulk copies need 16-byte aligned pencils and every rank must follow the same protocol: an odd user pointer is staged
+    if (pl->dev_in_bytes < first.in_bytes) {
+      if (pl->dev_in) p3dfftcu_free(pl->dev_in);
+      GPU(p3dfftcu_malloc(&pl->dev_in, (size_t)first.in_bytes), pl, "staging allocation");
+      pl->dev_in_bytes = first.in_bytes;
+    }
+    GPU(p3dfftcu_memcpy(pl->dev_in, ssrc, (size_t)first.in_bytes, 2, stream), pl, "device copy");
+    ssrc = pl->dev_in;
+  }
+  // group tables: chunk c of a stage = the range [c0, c1) of chunk_dim, everything along its other pencil dimension
+  p3dfftcu_sync sl, sx;
+  memset(&sl, 0, sizeof sl);
+  memset(&sx, 0, sizeof sx);
+  auto fill = [&](const StagePlan &st, p3dfftcu_sync &sy) {
+    sy.ngroups = (int)C;
+    const bool along_u = st.chunk_dim == st.u;
+    for (size_t c = 0; c < C; c++) {
+      p3dfftcu_group &g = sy.grp[c];
+      const int c0 = st.chunk_range[c].first, c1 = st.chunk_range[c].second;
+      g.u0 = along_u ? c0 : 0;
+      g.u1 = along_u ? c1 : (int)st.desc.nu;
+      g.v0 = along_u ? 0 : c0;
+      g.v1 = along_u ? (int)st.desc.nv : c1;
+      g.wait_id = g.signal_id = -1;
+    }
+  };
+  fill(L, sl);
+  fill(X, sx);
+  sl.ctl = pl->ctl;
+  sx.ctl = (char *)pl->ctl + 8 * 32;
+  GPU(p3dfftcu_memset(pl->ctl, 0, 8 * 64, stream), pl, "memset");
+  GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
+  GPU(p3dfftcu_stream_wait_event(xstream, ev[0]), pl, "stream wait");
+  peer_barrier(pl, X, xstream);  // every peer has finished reading its buffer w
+  const bool x_live = X.pair_handle && p3dfftcu_stage_sync_capable(X.pair_handle);
+  const bool l_live = L.pair_handle && p3dfftcu_stage_sync_capable(L.pair_handle);
+  if (l_first) {
+    // L publishes chunk c in this GPU's flag array, X waits for it
+    const unsigned long long le = ++ws.local_epoch;
+    for (size_t c = 0; c < C; c++) {
+      sl.grp[c].signal_id = (int)c;
+      sx.grp[c].wait_id = (int)c;
+    }
+    sl.sig_n = 1;
+    sl.sig_ptr[0] = (char *)ws.flags + 8 * WS_FLAG_LOCAL0;
+    sl.sig_epoch[0] = le;
+    sx.wait_n = 1;
+    sx.wait_base = ws.flags;
+    sx.wait_off[0] = WS_FLAG_LOCAL0;
+    sx.wait_epoch[0] = le;
+    void *d1[1] = {ws.buf[s & 1]};
+    if (l_live) GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ssrc, d1, 1, gL, stream, lcap, &sl), pl, "stage launch");
+    if (x_live) GPU(p3dfftcu_stage_exec_sync(X.pair_handle, ws.buf[s & 1], xdsts, np, gX, xstream, xcap, &sx), pl, "stage launch");
+    peer_barrier(pl, X, xstream);  // every peer's blocks have landed in my buffer w
+  } else {
+    // X publishes chunk c in every peer's flag array (row = my world rank), L waits for chunk c of every peer
+    int empty_ids[P3DFFTCU_MAXGRP], nempty = 0;
+    for (size_t c = 0; c < C; c++) {
+      sx.grp[c].signal_id = (int)c;
+      sl.grp[c].wait_id = (int)c;
+      const p3dfftcu_group &g = sx.grp[c];
+      if (!x_live || g.u1 <= g.u0 || g.v1 <= g.v0) empty_ids[nempty++] = (int)c;  // nothing to send: the host publishes it
+    }
+    sx.sig_n = sl.wait_n = np;
+    sl.wait_base = ws.flags;
+    for (int q = 0; q < np; q++) {
+      const int wr = peer_wr(pl, X, q);
+      const unsigned long long e = ++ws.epoch_with[wr];
+      sx.sig_ptr[q] = (char *)ws.peers[wr].flags + 8 * (WS_FLAG_GROUP0 + ws.world_rank * WS_FLAGS_PER_SRC);
+      sx.sig_epoch[q] = e;
+      sl.wait_off[q] = WS_FLAG_GROUP0 + wr * WS_FLAGS_PER_SRC;
+      sl.wait_epoch[q] = e;
+    }
+    if (nempty) GPU(p3dfftcu_flags_publish(sx.sig_ptr, sx.sig_epoch, np, empty_ids, nempty, xstream), pl, "flag publish");
+    if (x_live) GPU(p3dfftcu_stage_exec_sync(X.pair_handle, ssrc, xdsts, np, gX, xstream, xcap, &sx), pl, "stage launch");
+    void *d1[1] = {ldst};
+    if (l_live) {
+      GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ws.buf[w], d1, 1, gL, stream, lcap, &sl), pl, "stage launch");
+      // the SMs the exchange kernel leaves join the local stage (same tile counter) when its kernel hands tiles out dynamically
+      if (p3dfftcu_stage_sync_capable(L.pair_handle) == 2)
+        GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ws.buf[w], d1, 1, gL, xstream, xcap, &sl), pl, "stage launch");
+    }
+  }
+  GPU(p3dfftcu_event_record(ev[1], xstream), pl, "event");
+  GPU(p3dfftcu_stream_wait_event(stream, ev[1]), pl, "stream wait");
 }
 
 static void add_timer(const StagePlan &st, bool deriv, double sec) {
@@ -333,7 +527,8 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
       void *ldst = ls + 1 == S ? dst : ws.buf[ls & 1];
       if (l_first || (const void *)ldst != ssrc) {  // (in-place call whose output would overwrite X's input: run in sequence)
         const int dg[2] = {deriv_len(s), deriv_len(s + 1)};
-        run_pair(pl, s, ssrc, ldst, dg, stream);
+        if (st.pair_sync) run_pair_sync(pl, s, ssrc, ldst, dg, stream);
+        else run_pair(pl, s, ssrc, ldst, dg, stream);
         if (l_first && s + 2 == S)  // the exchange stage is the plan's last: its result sits in my work buffer
           GPU(p3dfftcu_memcpy(dst, ws.buf[(s + 1) & 1], (size_t)pl->stages[s + 1].out_bytes, 2, stream), pl, "device copy");
         if (timing) {  // the pair is timed as a whole: its duration is booked on the first stage, zero on the second
@@ -349,7 +544,7 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
     if (st.exchange) {
       const int w = (int)(s & 1);
       void *dsts[P3DFFTCU_MAXSEG];
-      for (size_t q = 0; q < st.peers.size(); q++) dsts[q] = ws.peer_buf[w][st.peers[q].peer_world];
+      for (size_t q = 0; q < st.peers.size(); q++) dsts[q] = ws.peers[peer_wr(pl, st, q)].buf[w];
       peer_barrier(pl, st, stream);  // every peer has finished reading its buffer w
       GPU(p3dfftcu_stage_exec(st.handle, ssrc, dsts, (int)st.peers.size(), deriv_g, stream), pl, "stage launch");
       peer_barrier(pl, st, stream);  // every peer's block has landed in my buffer w
@@ -357,7 +552,10 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
     } else {
       void *sdst = last ? dst : ws.buf[s & 1];
       const bool bounce = last && ssrc == (const void *)sdst;  // single stage, in == out
-      if (bounce) sdst = ws.buf[s & 1];
+      if (bounce) {
+        sdst = workspace_bounce(st.out_bytes);
+        if (!sdst) fatal(pl, "scratch allocation for an in-place single-stage transform");
+      }
       void *dsts[1] = {sdst};
       GPU(p3dfftcu_stage_exec(st.handle, ssrc, dsts, 1, deriv_g, stream), pl, "stage launch");
       if (bounce) GPU(p3dfftcu_memcpy(dst, sdst, (size_t)st.out_bytes, 2, stream), pl, "device copy");

@@ -60,7 +60,12 @@ struct StagePlan {
     long long in_off_bytes;  // byte offset of the chunk in the stage's input array
   };
   std::vector<Chunk> chunks;  // on BOTH stages of a pair, same count on every rank
-  StagePlan() : handle(nullptr), pair(PAIR_NONE), chunk_dim(-1) {}
+  // the same pair as ONE persistent launch per stage (tile groups = the chunks; wait / signal flags inside the kernels
+  // instead of one launch + one peer barrier per chunk): used when every rank's kernels have the tile-group form
+  std::vector<std::pair<int, int> > chunk_range;  // [c0, c1) of every chunk along chunk_dim on this rank
+  p3dfftcu_stage pair_handle;                     // the whole stage planned with CTAs that fill an SM
+  bool pair_sync;                                 // (on both stages) agreed by all ranks at plan time
+  StagePlan() : handle(nullptr), pair(PAIR_NONE), chunk_dim(-1), pair_handle(nullptr), pair_sync(false) {}
 };
 
 struct Plan {
@@ -69,6 +74,7 @@ struct Plan {
   int dt_in, dt_out;
   int nranks, rank;
   MPI_Comm comm;
+  std::vector<int> world_of;  // rank in comm -> rank in MPI_COMM_WORLD (the workspace's peer tables are keyed by world rank)
   DataGrid *g1, *g2;
   ProcGrid *pgrid;
   std::vector<StagePlan> stages;
@@ -86,6 +92,7 @@ struct Plan {
   // overlapped pairs: high-priority side stream for the exchange stage, fork/join and per-chunk events
   void *xstream;
   std::vector<void *> sync_events;
+  void *ctl;  // device words for the persistent pair kernels: two blocks of 32 (tile counter + group completion counts)
   Plan();
   ~Plan();
 };
@@ -93,20 +100,43 @@ struct Plan {
 std::string describe(const Plan &p);
 void plan_collect_times(Plan *p);
 
-// global device workspace shared by all plans: two ping-pong buffers, peer-mapped for the exchange
+// process-global device workspace shared by all plans: two ping-pong buffers and one flag array, mapped into the peers
+// with CUDA IPC.  Everything that names a peer is keyed by its rank in MPI_COMM_WORLD, so plans on different
+// (sub-)communicators neither alias each other's slots nor disturb each other's epochs.
+enum {
+  WS_MAX_RANKS = 64,
+  WS_FLAG_BARRIER0 = 0,                                         // [world rank]: peer barrier words
+  WS_FLAGS_PER_SRC = 32,
+  WS_FLAG_GROUP0 = WS_MAX_RANKS,                                // [source world rank][id]: tile-group flags set by peers
+  WS_FLAG_LOCAL0 = WS_FLAG_GROUP0 + WS_MAX_RANKS * WS_FLAGS_PER_SRC,  // [id]: tile-group flags between two kernels of this GPU
+  WS_FLAG_WORDS = WS_FLAG_LOCAL0 + 64
+};
+struct PeerMap {
+  void *buf[2];            // the peer's work buffers mapped here (own rank: the local pointers)
+  void *flags;             // its flag array
+  unsigned long long gen;  // generation of its buffers these mappings belong to (0 = not mapped)
+  PeerMap() : flags(nullptr), gen(0) { buf[0] = buf[1] = nullptr; }
+};
 struct Workspace {
   void *buf[2];
   long long bytes;
-  std::vector<void *> peer_buf[2];  // [which][world rank] mapped pointers (own rank = local pointer)
-  void *flags;                       // this rank's barrier flag array
-  std::vector<void *> peer_flags;    // [world rank]
-  unsigned long long epoch;
-  int nranks;
-  Workspace() : bytes(0), flags(nullptr), epoch(0), nranks(0) { buf[0] = buf[1] = nullptr; }
+  unsigned long long gen;        // grows every time this rank re-allocates its buffers
+  void *flags;                   // WS_FLAG_WORDS 8-byte words, allocated once
+  int world_rank, world_size;
+  std::vector<PeerMap> peers;    // [world rank]
+  // [world rank] number of barriers / flag-synchronised execs this rank has run TOGETHER with that rank: both sides count
+  // the same collective calls, so the value is the epoch both expect
+  std::vector<unsigned long long> epoch_with;
+  unsigned long long local_epoch;  // flags between two kernels of this GPU
+  std::vector<void *> retired;     // old buffers a rank outside the reserving communicator may still have mapped
+  Workspace() : bytes(0), gen(0), flags(nullptr), world_rank(0), world_size(0), local_epoch(0) { buf[0] = buf[1] = nullptr; }
 };
 Workspace &workspace();
-// collective over comm: make the workspace at least `bytes` per buffer on every rank
-bool workspace_reserve(long long bytes, MPI_Comm comm, int nranks, int rank, std::string *err);
+// collective over comm: make the workspace at least `bytes` per buffer on every rank of comm and (re-)map the members'
+// buffers; fails on all ranks together
+bool workspace_reserve(long long bytes, MPI_Comm comm, int nranks, int rank, std::string *err, std::vector<int> *world_of);
+// lazily grown local scratch of this rank alone (single-stage in == out calls)
+void *workspace_bounce(long long bytes);
 void workspace_release();
 
 bool gpu_ready();

@@ -413,28 +413,63 @@ bool plan_overlap(Plan *pl, const std::vector<ProtoStage> &protos) {
     if (align < 1) align = 1;
     cs = (cs + align - 1) / align * align;
     if (cs <= 0 || rep < 2 * cs) continue;  // too small to be worth cutting
-    const int C = (rep + cs - 1) / cs;
     const int mine = mode == StagePlan::PAIR_L_THEN_X ? X.in.ldims[cdim] : X.out.ldims[cdim];
     StagePlan &first = mode == StagePlan::PAIR_L_THEN_X ? L : X;
     first.pair = mode;
     L.chunk_dim = X.chunk_dim = cdim;
+    // one persistent launch per stage (tile groups + flags) when the kernels of BOTH stages have that form on EVERY rank
+    // (a rank without local pencils counts as capable); otherwise one launch + one peer barrier per chunk
+    bool sync_ok = env_int("P3DFFT_B200_PAIR_SYNC", 1) != 0;
+    StagePlan *both[2] = {&L, &X};
+    for (int i = 0; i < 2 && sync_ok; i++) {
+      p3dfftcu_stage_desc d = both[i]->desc;
+      d.whole_sm_ctas = 1;  // the two kernels split the SMs by CTA count
+      if (p3dfftcu_stage_create(&d, &both[i]->pair_handle)) {
+        pl->error = std::string("pair stage setup failed: ") + p3dfftcu_last_error();
+        return false;
+      }
+      const bool empty = d.nu <= 0 || d.nv <= 0 || d.n_in <= 0;
+      if (!empty && !p3dfftcu_stage_sync_capable(both[i]->pair_handle)) sync_ok = false;
+    }
+    int ok_l = sync_ok ? 1 : 0, ok_g = ok_l;
+    MPI_Allreduce(&ok_l, &ok_g, 1, MPI_INT, MPI_MIN, pl->comm);
+    L.pair_sync = X.pair_sync = ok_g != 0;
+    // chunk boundaries (rank-independent, clipped to this rank's block below).  With flags a chunk costs nothing, so the
+    // first and the last full chunk are halved: the pipeline fills and drains on half a chunk
+    std::vector<int> bnd;
+    const int C0 = (rep + cs - 1) / cs;
+    const bool halves = L.pair_sync && env_int("P3DFFT_B200_PAIR_HALVES", 1) && cs % 2 == 0 && (cs / 2) % std::max(1, align / 2) == 0 &&
+                        C0 >= 2 && C0 + 2 <= P3DFFTCU_MAXGRP && C0 + 2 <= WS_FLAGS_PER_SRC;
+    for (int c = 0; c <= C0; c++) {
+      bnd.push_back(c * cs);
+      if (halves && (c == 0 || c == C0 - 1)) bnd.push_back(c * cs + cs / 2);
+    }
+    const int C = (int)bnd.size() - 1;
     L.chunks.resize(C);
     X.chunks.resize(C);
-    for (int c = 0; c < C; c++) {
-      const int c0 = std::min(c * cs, mine), c1 = std::min((c + 1) * cs, mine);
-      if (!make_chunk(L, pl->prec, cdim, c0, c1, &L.chunks[c], &pl->error)) return false;
-      if (!make_chunk(X, pl->prec, cdim, c0, c1, &X.chunks[c], &pl->error)) return false;
-    }
+    L.chunk_range.resize(C);
+    X.chunk_range.resize(C);
+    for (int c = 0; c < C; c++) L.chunk_range[c] = X.chunk_range[c] = std::make_pair(std::min(bnd[c], mine), std::min(bnd[c + 1], mine));
+    if (!L.pair_sync)
+      for (int c = 0; c < C; c++) {
+        const int c0 = L.chunk_range[c].first, c1 = L.chunk_range[c].second;
+        if (!make_chunk(L, pl->prec, cdim, c0, c1, &L.chunks[c], &pl->error)) return false;
+        if (!make_chunk(X, pl->prec, cdim, c0, c1, &X.chunks[c], &pl->error)) return false;
+      }
     used[x] = used[l] = true;
   }
   bool any = false;
   for (size_t s = 0; s < S; s++) any = any || pl->stages[s].pair != StagePlan::PAIR_NONE;
   if (any) {
+    if (p3dfftcu_malloc(&pl->ctl, 8 * 64)) {
+      pl->error = std::string("pair control block: ") + p3dfftcu_last_error();
+      return false;
+    }
     if (p3dfftcu_stream_create(&pl->xstream, 1)) {
       pl->error = std::string("side stream: ") + p3dfftcu_last_error();
       return false;
     }
-    for (int i = 0; i < 2 + 16; i++) {
+    for (int i = 0; i < 2 + P3DFFTCU_MAXGRP; i++) {
       void *e = nullptr;
       if (p3dfftcu_event_create(&e)) {
         pl->error = std::string("event: ") + p3dfftcu_last_error();
@@ -485,13 +520,17 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
       if (ok) pl->error = "stage setup failed on another rank";
       return false;
     }
+    // a single local stage writes straight into the user's array: no work buffers (an in == out call takes a lazily
+    // allocated scratch, executor.cpp)
     bool need_ws = S > 1 || pl->nranks > 1;
     for (size_t s = 0; s < S; s++) need_ws = need_ws || pl->stages[s].exchange;
     std::string err;
-    if (!workspace_reserve(pl->work_bytes, pl->comm, pl->nranks, pl->rank, &err)) {
-      pl->error = err;
-      return false;
-    }
+    if (need_ws) {
+      if (!workspace_reserve(pl->work_bytes, pl->comm, pl->nranks, pl->rank, &err, &pl->world_of)) {
+        pl->error = err;
+        return false;
+      }
+    } else pl->world_of.assign(1, 0);
   }
   return true;
 }
@@ -500,17 +539,19 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
 
 Plan::Plan()
     : ok(false), prec(0), dt_in(0), dt_out(0), nranks(1), rank(0), comm(MPI_COMM_NULL), g1(nullptr), g2(nullptr), pgrid(nullptr),
-      in_bytes(0), out_bytes(0), work_bytes(0), timed_execs(0), events_valid(false), last_deriv_stage(-1), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0), xstream(nullptr) {}
+      in_bytes(0), out_bytes(0), work_bytes(0), timed_execs(0), events_valid(false), last_deriv_stage(-1), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0), xstream(nullptr), ctl(nullptr) {}
 
 Plan::~Plan() {
   for (size_t s = 0; s < stages.size(); s++) {
     if (stages[s].handle) p3dfftcu_stage_destroy(stages[s].handle);
+    if (stages[s].pair_handle) p3dfftcu_stage_destroy(stages[s].pair_handle);
     for (size_t c = 0; c < stages[s].chunks.size(); c++)
       if (stages[s].chunks[c].handle) p3dfftcu_stage_destroy(stages[s].chunks[c].handle);
   }
   for (size_t i = 0; i < events.size(); i++) p3dfftcu_event_destroy(events[i]);
   for (size_t i = 0; i < sync_events.size(); i++) p3dfftcu_event_destroy(sync_events[i]);
   if (xstream) p3dfftcu_stream_destroy(xstream);
+  if (ctl) p3dfftcu_free(ctl);
   if (dev_in) p3dfftcu_free(dev_in);
   if (dev_out) p3dfftcu_free(dev_out);
   delete g1;
@@ -711,7 +752,9 @@ std::string describe(const Plan &p) {
     put3(o, "out_ldims", st.out.ldims);
     o << ",";
     put3(o, "out_mo", st.out.mo);
-    o << ",\"pair\":" << st.pair << ",\"chunk_dim\":" << st.chunk_dim << ",\"chunks\":" << st.chunks.size();
+    o << ",\"pair\":" << st.pair << ",\"chunk_dim\":" << st.chunk_dim << ",\"chunks\":" << st.chunks.size()
+      << ",\"pair_sync\":" << (st.pair_sync ? "true" : "false");
+    if (st.pair_handle) o << ",\"pair_variant\":\"" << p3dfftcu_stage_variant(st.pair_handle) << "\"";
     o << ",\"variant\":\"" << (st.handle ? p3dfftcu_stage_variant(st.handle) : "") << "\",\"segs\":[";
     for (int q = 0; q < st.desc.nseg; q++) {
       const p3dfftcu_seg &g = st.desc.seg[q];

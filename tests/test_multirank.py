@@ -47,6 +47,7 @@ def launch(nranks, cases, mode="emu", gloo=False, timeout=900, env_extra=None):
                os.path.join(HERE, "mp_worker.py"), mode, arg]
     env = dict(os.environ)
     env.pop("P3DFFT_B200_PLAN_ONLY", None)
+    env.setdefault("P3DFFT_B200_PEER_TIMEOUT_S", "120")  # a rank that dies must fail the others instead of hanging them
     env.update(env_extra or {})
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     ok = out.returncode == 0 and out.stdout.count(" OK worst") == nranks
@@ -167,6 +168,24 @@ def test_overlapped_exchange_pairs():
     launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2])], env_extra={"P3DFFT_B200_OVERLAP": "0"})
 
 
+SYNC_PAIRS = {"P3DFFT_TEST_EXPECT_PAIRS": "1", "P3DFFT_TEST_EXPECT_SYNC": "1"}
+
+
+def test_persistent_pair_kernels_with_flags():
+    """overlapped pairs as ONE persistent launch per stage: the chunks are tile groups, "chunk complete" is a flag word written
+    inside the producing kernel (local stage -> exchange stage on this rank; exchange stage -> every peer's local stage) and
+    awaited inside the consuming one.  Slab forward (L then X) and backward (X then L), uneven blocks over 3 ranks, pencil
+    grid, fused derivative in either member, in-place"""
+    n = (128, 64, 64)
+    launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2]), fwd(n, [1, 1, 2], deriv=1), fwd(n, [1, 1, 2], deriv=0),
+               c2c((64, 64, 64), [1, 1, 2], inplace=True)], env_extra=SYNC_PAIRS, timeout=1500)
+    small = dict(SYNC_PAIRS, P3DFFT_B200_OVERLAP_ALIGN="1", P3DFFT_B200_OVERLAP_CHUNKS="3")
+    launch(3, [fwd((128, 64, 20), [1, 1, 3], reps=2), bwd((128, 64, 64), [1, 1, 3], reps=2)], env_extra=small, timeout=1500)
+    launch(4, [fwd((128, 64, 64), [1, 2, 2], reps=1), bwd((128, 64, 64), [1, 2, 2], reps=1)], env_extra=small, timeout=1500)
+    launch(2, [fwd(n, [1, 1, 2], reps=1), bwd(n, [1, 1, 2], reps=1)], env_extra={"P3DFFT_B200_PAIR_SYNC": "0", "P3DFFT_TEST_EXPECT_PAIRS": "1"},
+           timeout=1500)
+
+
 # ------------------------------------------------------------------------------------------------ real GPUs
 def _ngpu():
     try:
@@ -179,9 +198,11 @@ def _ngpu():
 @pytest.mark.gpu
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_gpu_multirank_parity(nranks):
-    """the same cases on N real GPUs (one process per GPU, peer stores over NVLink); skipped when the box has fewer"""
-    if _ngpu() < nranks:
-        pytest.skip(f"needs {nranks} GPUs")
+    """the same cases on N real GPUs (one process per GPU, peer stores over NVLink).  On a box with fewer GPUs the ranks
+    share the devices (rank r -> device r mod count; CUDA IPC maps buffers between processes of one device as well, the
+    contexts are time-sliced), so the exchange kernels, peer barriers and overlapped pairs run on hardware whatever the box"""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
     n = (128, 96, 64)
     grids = [[1, 1, nranks]] + ([[1, 2, nranks // 2]] if nranks >= 4 else [[1, nranks, 1]])
     cs = []
@@ -192,6 +213,34 @@ def test_gpu_multirank_parity(nranks):
     launch(nranks, cs, mode="gpu", timeout=1200)
     if nranks == 4:
         launch(4, "golden", mode="gpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_gpu_overlapped_pairs_parity(nranks):
+    """shapes large enough to plan overlapped pairs WITHOUT lifting the chunk alignment (the production configuration of the
+    1024^3 runs): persistent pair kernels with tile-group flags (asserted), then the same cases with one launch + one peer
+    barrier per chunk (P3DFFT_B200_PAIR_SYNC=0); slab and pencil grids, single precision, fused derivative"""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    n = (256, 128, 32 * nranks)
+    pd = [1, 1, nranks]
+    cs = [fwd(n, pd), bwd(n, pd), fwd(n, pd, types=RCC_S), fwd(n, pd, deriv=1), fwd(n, pd, deriv=0), c2c((128, 128, 32 * nranks), pd)]
+    launch(nranks, cs, mode="gpu", timeout=1200, env_extra=SYNC_PAIRS)
+    launch(nranks, cs[:2], mode="gpu", timeout=1200, env_extra={"P3DFFT_B200_PAIR_SYNC": "0", "P3DFFT_TEST_EXPECT_PAIRS": "1"})
+    if nranks >= 4:
+        pp = [1, 2, nranks // 2]
+        m = (256, 128, 64 * (nranks // 2))
+        launch(nranks, [fwd(m, pp), bwd(m, pp)], mode="gpu", timeout=1200, env_extra={"P3DFFT_TEST_EXPECT_PAIRS": "1"})
+
+
+@pytest.mark.gpu
+def test_gpu_overlapped_pairs_512x512x256():
+    """4 ranks, 512 x 512 x 256 double: eight chunks per pair as in the headline runs, against the oracle"""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    n = (512, 512, 256)
+    launch(4, [fwd(n, [1, 1, 4], reps=2), bwd(n, [1, 1, 4], reps=2)], mode="gpu", timeout=1500, env_extra=SYNC_PAIRS)
 
 
 @pytest.mark.parametrize("switch", ["P3DFFT_B200_NO_PAD", "P3DFFT_B200_NO_PIPE", "P3DFFT_B200_NO_FASTCORE", "P3DFFT_B200_FORCE_GENERIC"])

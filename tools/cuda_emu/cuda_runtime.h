@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -54,7 +55,7 @@ template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiproces
 namespace p3b { extern unsigned char smem_raw[]; }
 
 // run `grid` blocks one after another, each with `block` OS threads
-template <class Kernel, class Params> void emu_launch(Kernel k, int grid, int block, size_t smem, const Params &P) {
+template <class Kernel, class... Params> void emu_launch(Kernel k, int grid, int block, size_t smem, const Params &...P) {
   if (smem > 232448) { fprintf(stderr, "emu: shared memory request too large\n"); abort(); }
   gridDim.x = grid; gridDim.y = gridDim.z = 1;
   blockDim.x = block; blockDim.y = blockDim.z = 1;
@@ -66,13 +67,14 @@ template <class Kernel, class Params> void emu_launch(Kernel k, int grid, int bl
     for (int t = 0; t < block; t++)
       th.emplace_back([&, t]() {
         threadIdx.x = t; threadIdx.y = threadIdx.z = 0;
-        k(P);
+        k(P...);
       });
     for (auto &x : th) x.join();
     pthread_barrier_destroy(&emu_block_barrier);
   }
 }
 #define P3B_LAUNCH(kernel, grid, block, smem, stream, params) emu_launch(kernel, (grid) < 2 ? (grid) : 2, block, smem, params)
+#define P3B_LAUNCH2(kernel, grid, block, smem, stream, p1, p2) emu_launch(kernel, (grid) < 2 ? (grid) : 2, block, smem, p1, p2)
 
 // ---- host runtime stubs: "device" memory is plain host memory
 struct cudaDeviceProp { char name[64]; int major, minor, multiProcessorCount; size_t sharedMemPerBlockOptin; };
