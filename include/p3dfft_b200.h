@@ -123,11 +123,17 @@ typedef struct p3dfftcu_group {
   int u0, u1, v0, v1;
   int wait_id;   /* >= 0: flag id that every wait source must have published; < 0: no wait */
   int signal_id; /* >= 0: flag id published to every signal target on completion; < 0: none */
+  int count;     /* != 0: count the group's completed pencils although it publishes nothing (see `after`) */
+  int after;     /* publish only once the groups [0, after) are complete as well (they must count or signal) */
 } p3dfftcu_group;
 typedef struct p3dfftcu_sync {
   int ngroups;
   p3dfftcu_group grp[P3DFFTCU_MAXGRP];
   void *ctl;
+  /* kernels that take their work from the counter only (p3dfftcu_stage_sync_capable() == 2): launch with up to boost_ctas
+   * CTAs (<= 0: no boost); those beyond max_ctas retire once the first boost_groups groups have been handed out, so the
+   * stage starts on the whole GPU and then leaves room for its partner kernel */
+  int boost_ctas, boost_groups;
   int wait_n;                             /* wait sources: flag word (j, id) = ((uint64*)wait_base)[wait_off[j] + id] */
   const void *wait_base;
   int wait_off[P3DFFTCU_MAXSEG];

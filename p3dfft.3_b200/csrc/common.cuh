@@ -85,10 +85,15 @@ struct TileGroupDev {
   long long tile0;       // global number of its first tile
   int wait_id;           // >= 0: flag id every wait source must have published before the group is loaded
   int signal_id;         // >= 0: flag id published to every signal target when the group is complete
+  int count;             // != 0: completed pencils are counted in ctl[1 + g] (implied by signal_id >= 0)
+  int after;             // the flag is published only once the groups [0, after) are complete as well (they must count)
 };
 struct SyncDev {
   int ngroups;
-  int dynamic;                  // tiles come from the counter ctl[0] instead of blockIdx striding (TS = 1 kernels)
+  int dynamic;                  // work comes from the counter ctl[0] instead of blockIdx striding: whole tiles (transposed-output
+                                // kernels, one CTA barrier per tile anyway) or single pencils (contiguous-output kernels)
+  int keep_ctas;                // dynamic only: CTAs >= keep_ctas stop taking work once the counter has reached boost_limit
+  unsigned long long boost_limit;  //   (the stage starts on every SM and then leaves room for its partner kernel)
   unsigned long long *ctl;      // [0] tile counter, [1 + g] pencils of group g completed (zeroed by the host before the launch)
   unsigned long long timeout_ns;  // > 0: trap when a wait lasts longer (0 = wait for ever)
   const unsigned long long *wait_base;  // word of (source j, id) = wait_base[wait_off[j] + id]

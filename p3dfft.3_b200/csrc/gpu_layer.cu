@@ -751,7 +751,13 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
 // share one control block share the work)
 int p3dfftcu_stage_sync_capable(p3dfftcu_stage st) {
   if (st->empty || st->variant != V_PIPE || st->pp.ntiles <= 0) return 0;
-  return st->pp.ld ? 2 : 1;
+  if (st->pp.ld) return 2;  // transposed output: one CTA barrier per tile anyway, whole tiles are handed out
+#ifdef P3B_EMU
+  return 1;  // (the emulation's group barriers are CTA barriers: thread groups cannot take different numbers of pencils)
+#else
+  // contiguous output: a pencil's thread group takes single pencils, provided it is made of whole warps
+  return st->pp.info->threads / st->pp.P >= 32 ? 2 : 1;
+#endif
 }
 
 int p3dfftcu_stage_exec_sync(p3dfftcu_stage st, const void *in, void *const *dst, int ndst, int deriv_g, void *stream,
@@ -776,7 +782,8 @@ int p3dfftcu_stage_exec_sync(p3dfftcu_stage st, const void *in, void *const *dst
   SyncDev Y;
   memset(&Y, 0, sizeof Y);
   Y.ngroups = sy->ngroups;
-  Y.dynamic = pp.ld ? 1 : 0;  // the transposed-output kernels synchronise the CTA once per tile: tiles from a counter
+  Y.dynamic = p3dfftcu_stage_sync_capable(st) == 2 ? 1 : 0;
+  Y.keep_ctas = 1 << 30;
   Y.ctl = (unsigned long long *)sy->ctl;
   Y.timeout_ns = g_peer_timeout_ns;
   Y.wait_base = (const unsigned long long *)sy->wait_base;
@@ -796,18 +803,27 @@ int p3dfftcu_stage_exec_sync(p3dfftcu_stage st, const void *in, void *const *dst
     D.tile0 = t0;
     D.wait_id = G.wait_id;
     D.signal_id = G.signal_id;
+    D.count = G.count;
+    D.after = G.after;
     t0 += (long long)D.tiles_u * D.tiles_v;
   }
   P.ntiles = t0;
   if (t0 == 0) return 0;
+  const long long per_tile = (Y.dynamic && !pp.ld) ? pp.P : 1;  // contiguous-output kernels hand out single pencils
   int grid;
   {
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp.info->func_sync, pp.info->threads, pp.info->smem) != cudaSuccess || occ < 1) occ = 1;
     grid = g_num_sms * occ;
   }
-  if (t0 < grid) grid = (int)t0;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (t0 * per_tile < grid) grid = (int)(t0 * per_tile);
+  if (max_ctas > 0 && grid > max_ctas) {
+    if (Y.dynamic && sy->boost_ctas > max_ctas && sy->boost_groups > 0 && sy->boost_groups < sy->ngroups) {
+      Y.keep_ctas = max_ctas;
+      Y.boost_limit = (unsigned long long)(Y.grp[sy->boost_groups].tile0 * per_tile);
+      if (grid > sy->boost_ctas) grid = sy->boost_ctas;
+    } else grid = max_ctas;
+  }
   pp.info->launch_sync(P, Y, grid, (cudaStream_t)stream);
   g_launches++;
   CK(cudaGetLastError());

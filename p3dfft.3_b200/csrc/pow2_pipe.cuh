@@ -135,12 +135,18 @@ __device__ __forceinline__ bool flags_ready(const SyncDev &Y, int id, bool block
 
 // `add` pencils of group g are complete (the caller has synchronised the threads that stored them): count them, and publish
 // the group's flag to every target when it was the last contribution
-__device__ __forceinline__ void group_done(const SyncDev &Y, int g, unsigned long long add, unsigned long long total) {
+template <int P> __device__ __forceinline__ void group_done(const SyncDev &Y, int g, unsigned long long add) {
+  const unsigned long long total = (unsigned long long)Y.grp[g].tiles_u * Y.grp[g].tiles_v * P;
   fence_sys();
   const unsigned long long prev = ctr_add(Y.ctl + 1 + g, add);
-  if (prev + add == total) {
+  const int id = Y.grp[g].signal_id;
+  if (prev + add == total && id >= 0) {
+    // groups handed out earlier may still have a tile in flight on another CTA: wait for their counters
+    for (int h = 0; h < Y.grp[g].after; h++) {
+      const unsigned long long th = (unsigned long long)Y.grp[h].tiles_u * Y.grp[h].tiles_v * P;
+      while (flag_ld(Y.ctl + 1 + h) < th) spin_pause();
+    }
     fence_sys();
-    const int id = Y.grp[g].signal_id;
     for (int j = 0; j < Y.sig_n; j++) flag_st(Y.sig_ptr[j] + id, Y.sig_epoch[j]);
   }
 }
@@ -170,7 +176,7 @@ template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
   // the banks; XP0 = M + M/16 + 1 is odd
   enum { PITCH = sizeof(T) == 8 ? XP0 : ((XP0 + 1) % 4 == 2 ? XP0 + 1 : XP0 + 3) };
   enum { T2N = R1 * R2, T3N = R3 > 1 ? R3 * TP : 0 };
-  static constexpr size_t bar_bytes = 256;  // P mbarriers (<= 128 bytes), then two words for the tile numbers handed out dynamically
+  static constexpr size_t bar_bytes = 384;  // P mbarriers (<= 128 bytes), then 2 x 16 words for the work items handed out dynamically
   static constexpr size_t smem = bar_bytes + ((size_t)P * PITCH + T2N + T3N) * csz;
   static constexpr bool valid = (THREADS >= 32) && (THREADS <= 1024) && (P <= 16) && (smem <= kPipeSmemMax) && (TS ? P >= 2 : true) &&
                                 (TP > 32 ? P <= 15 : true);
@@ -311,8 +317,8 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
   // the output is contiguous along the transform dimension, else the lanes run across the tile's pencils
   const int slotA = tid / TP, tA = tid % TP;
   const int slotB = TS ? tid % P : slotA, tB = TS ? tid / P : tA;
-  const int puA = slotA & (tile_u - 1), pvA = slotA >> tu_log2;
-  const int puB = slotB & (tile_u - 1), pvB = slotB >> tu_log2;
+  int puA = slotA & (tile_u - 1), pvA = slotA >> tu_log2;  // (re-derived per work item when pencils are handed out singly)
+  int puB = slotB & (tile_u - 1), pvB = slotB >> tu_log2;
   C *BA = B + slotA * PITCH, *BB = B + slotB * PITCH;
   unsigned long long *bar = bars + slotA;
   auto syncA = [&]() {  // the threads of one pencil (whole warps, or a fraction of one warp)
@@ -349,14 +355,31 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
   };
   int gI = 0, gReady = -1;  // leaders: group of the tile being issued; groups <= gReady have had their flag seen
   long long pend = -1;      // leaders: tile whose load waits for its group's flag (issued, blocking, at the top of the loop)
-  auto issue = [&](long long tl, bool blocking) {
-    if (tA == 0 && tl < Q.ntiles) {
+  // SY, contiguous output, dynamic: the unit of work is ONE pencil (a pencil's thread group never synchronises with the others):
+  // work item w = pencil w % P of tile w / P
+  bool dynamic = false, dynp = false;
+  if constexpr (SY) {
+    dynamic = Yp->dynamic != 0;
+    dynp = dynamic && !TS;
+  }
+  const long long nwork = dynp ? Q.ntiles * P : Q.ntiles;
+  auto issue = [&](long long wl, bool blocking) {
+    if (tA == 0 && wl < nwork) {
+      long long tl = wl;
+      if constexpr (SY && !TS) {
+        if (dynp) {
+          tl = wl / P;
+          const int ps = (int)(wl % P);
+          puA = ps & (tile_u - 1);
+          pvA = ps >> tu_log2;
+        }
+      }
       if constexpr (SY) {
         gI = group_of(tl, gI);
         if (gI > gReady) {
           const int wid = Yp->grp[gI].wait_id;
           if (wid >= 0 && !flags_ready(*Yp, wid, blocking)) {
-            pend = tl;
+            pend = wl;
             return;
           }
           gReady = gI;
@@ -384,24 +407,43 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
   if constexpr (c2r) wt = tw[tA];
 
   if (tid < P) mbar_init(bars + tid, 1);
-  bool dynamic = false;
-  if constexpr (SY && TS) dynamic = Yp->dynamic != 0;
+  // next work item from the counter; CTAs beyond keep_ctas stop once the counter has passed boost_limit (checked BEFORE
+  // taking an item: whatever was taken is processed)
+  auto grab = [&]() -> long long {
+    if constexpr (SY) {
+      if ((int)blockIdx.x >= Yp->keep_ctas && flag_ld(Yp->ctl) >= Yp->boost_limit) return (long long)1 << 60;
+      return (long long)ctr_add(Yp->ctl, 1ull);
+    }
+    return 0;
+  };
+  // the slot a handed-out item travels through: one per CTA (TS) or one per pencil's thread group, double-buffered
+  long long *sn = snext + (TS ? 0 : 2 * slotA);
   if constexpr (SY)
-    if (dynamic && tid == 0) snext[0] = (long long)ctr_add(Yp->ctl, 1ull);
+    if (dynamic && (TS ? tid == 0 : tA == 0)) sn[0] = grab();
   __syncthreads();
 
-  long long tile = blockIdx.x;
+  long long work = blockIdx.x;  // tile number, or pencil number when pencils are handed out singly
   if constexpr (SY)
-    if (dynamic) tile = snext[0];
+    if (dynamic) work = sn[0];
   unsigned parity = 0;
   int gS = 0, it = 0;            // SY: group of the tile being processed; iteration count
   unsigned long long cnt = 0;    // SY: pencils of group gS this thread has to account for
-  issue(tile, true);
-  while (tile < Q.ntiles) {
-    long long nxt = tile + gridDim.x;
+  issue(work, true);
+  while (work < nwork) {
+    long long nxt = work + gridDim.x;
+    long long tile = work;
+    if constexpr (SY && !TS) {
+      if (dynp) {
+        tile = work / P;
+        const int ps = (int)(work % P);
+        puA = puB = ps & (tile_u - 1);
+        pvA = pvB = ps >> tu_log2;
+      }
+    }
     if constexpr (SY) {
       gS = group_of(tile, gS);
-      if (dynamic && tid == 0) snext[(it + 1) & 1] = (long long)ctr_add(Yp->ctl, 1ull);  // read after the next CTA barrier
+      // read back after the next barrier of the CTA (TS) / of the pencil's thread group
+      if (dynamic && (TS ? tid == 0 : tA == 0)) sn[(it + 1) & 1] = grab();
       if (tA == 0 && pend >= 0) {  // the prefetch found the group's flag not yet set: wait for it now
         const long long t = pend;
         pend = -1;
@@ -466,7 +508,7 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
         }
       }
       syncB();  // every value is in registers: the buffers are free for the next tile
-      if constexpr (SY) if (dynamic) nxt = snext[(it + 1) & 1];
+      if constexpr (SY) if (dynamic) nxt = sn[(it + 1) & 1];
       issue(nxt, false);
       C w3[R3];  // w_M^{q t}
 #pragma unroll
@@ -525,7 +567,7 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
     smem_gather<T, M, E>(v, BB, tB);  // re-maps to the store side when TS
     if constexpr (!r2c) {
       syncB();  // every value is back in registers: the buffers are free for the next tile
-      if constexpr (SY) if (dynamic) nxt = snext[(it + 1) & 1];
+      if constexpr (SY) if (dynamic) nxt = sn[(it + 1) & 1];
       issue(nxt, false);
     }
     if constexpr (R3 > 1) reg_pass3<T, M, E, R3>(v, tB, T3);
@@ -556,7 +598,7 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
         if (m == 0) xM = mk<T>(zk.x - zk.y, (T)0);  // X[M], used by the thread that owns k = 0
       }
       syncB();
-      if constexpr (SY) if (dynamic) nxt = snext[(it + 1) & 1];
+      if constexpr (SY) if (dynamic) nxt = sn[(it + 1) & 1];
       issue(nxt, false);
       if (live) {
         if (Q.nseg == 1 && Q.deriv_g <= 0) {  // local stage: one base pointer, constant stride between a thread's stores
@@ -604,28 +646,27 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
     if constexpr (SY) {
       // a group that signals: count this tile's pencils; when the CTA (TS) or the pencil's thread group (!TS) leaves the
       // group, add them to the group's counter -- whoever completes it publishes the flag
-      if (Yp->grp[gS].signal_id >= 0) {
-        const bool leaving = nxt >= Q.ntiles || group_of(nxt, gS) != gS;
-        const unsigned long long total = (unsigned long long)Yp->grp[gS].tiles_u * Yp->grp[gS].tiles_v * P;
+      if (Yp->grp[gS].signal_id >= 0 || Yp->grp[gS].count) {
+        const bool leaving = nxt >= nwork || group_of(dynp ? nxt / P : nxt, gS) != gS;
         if (TS) {
           cnt += P;
           if (leaving) {
             __syncthreads();
-            if (tid == 0) group_done(*Yp, gS, cnt, total);
+            if (tid == 0) group_done<P>(*Yp, gS, cnt);
             cnt = 0;
           }
         } else {
           cnt += 1;
           if (leaving) {
             syncA();
-            if (tA == 0) group_done(*Yp, gS, cnt, total);
+            if (tA == 0) group_done<P>(*Yp, gS, cnt);
             cnt = 0;
           }
         }
       }
       it++;
     }
-    tile = nxt;
+    work = nxt;
   }
 }
 

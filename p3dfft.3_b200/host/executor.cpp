@@ -337,7 +337,8 @@ static void run_pair(Plan *pl, size_t s, const void *ssrc, void *ldst, const int
 // GPU's flag array when the local stage feeds the exchange stage, to every peer's over NVLink when the exchange stage
 // feeds the peers' local stages) and is awaited by the thread that issues the consuming kernel's bulk loads.  No launch and
 // no barrier kernel per chunk; the CTAs freed by the exchange kernel join the local stage's tile pool.
-static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, const int deriv_g[2], void *stream) {
+// (zdst != nullptr: the L -> X -> Z triple of plan.h, Z writing zdst)
+static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, const int deriv_g[3], void *stream, void *zdst) {
   Workspace &ws = g_ws;
   StagePlan &first = pl->stages[s], &second = pl->stages[s + 1];
   const bool l_first = first.pair == StagePlan::PAIR_L_THEN_X;
@@ -384,19 +385,107 @@ static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, cons
   fill(X, sx);
   sl.ctl = pl->ctl;
   sx.ctl = (char *)pl->ctl + 8 * 32;
-  GPU(p3dfftcu_memset(pl->ctl, 0, 8 * 64, stream), pl, "memset");
+  GPU(p3dfftcu_memset(pl->ctl, 0, 8 * 96, stream), pl, "memset");
+  static const int sms = p3dfftcu_num_sms();
   GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
   GPU(p3dfftcu_stream_wait_event(xstream, ev[0]), pl, "stream wait");
   peer_barrier(pl, X, xstream);  // every peer has finished reading its buffer w
   const bool x_live = X.pair_handle && p3dfftcu_stage_sync_capable(X.pair_handle);
   const bool l_live = L.pair_handle && p3dfftcu_stage_sync_capable(L.pair_handle);
-  if (l_first) {
+  if (l_first && X.triple && zdst) {
+    // three kernels: L (z-chunks) -> X (first the leading z-chunks behind L, then the rest of z piece by piece along L's
+    // transform dimension a, each piece published to the peers) -> Z (piece k once every peer has published it)
+    StagePlan &Z = pl->stages[s + 2];
+    const int c1 = X.tri_c1, K = (int)X.tri_a_range.size(), a = L.dim;
+    const unsigned long long le = ++ws.local_epoch;
+    // L: chunks [0, c1) as they are, the remaining chunks merged into one group
+    const bool l_u = L.chunk_dim == L.u;
+    sl.ngroups = c1 + 1;
+    {
+      p3dfftcu_group &g = sl.grp[c1];
+      const int z0 = L.chunk_range[c1].first, z1 = L.chunk_range[C - 1].second;
+      g.u0 = l_u ? z0 : 0;
+      g.u1 = l_u ? z1 : (int)L.desc.nu;
+      g.v0 = l_u ? 0 : z0;
+      g.v1 = l_u ? (int)L.desc.nv : z1;
+    }
+    for (int c = 0; c <= c1; c++) sl.grp[c].signal_id = c;
+    sl.sig_n = 1;
+    sl.sig_ptr[0] = (char *)ws.flags + 8 * WS_FLAG_LOCAL0;
+    sl.sig_epoch[0] = le;
+    sl.boost_ctas = sms;
+    sl.boost_groups = 1;
+    // X: chunks [0, c1) wait for L's flags and are counted; then K pieces (a-range x remaining z) wait for L's last group
+    const bool x_u = X.chunk_dim == X.u;  // (the other pencil dimension of X is a)
+    sx.ngroups = c1 + K;
+    for (int c = 0; c < c1; c++) {
+      sx.grp[c].wait_id = c;
+      sx.grp[c].count = 1;
+    }
+    int empty_ids[P3DFFTCU_MAXGRP], nempty = 0;
+    const int z0 = X.chunk_range[c1].first, z1 = X.chunk_range[C - 1].second;
+    for (int k = 0; k < K; k++) {
+      p3dfftcu_group &g = sx.grp[c1 + k];
+      const int a0 = X.tri_a_range[k].first, a1 = X.tri_a_range[k].second;
+      g.u0 = x_u ? z0 : a0;
+      g.u1 = x_u ? z1 : a1;
+      g.v0 = x_u ? a0 : z0;
+      g.v1 = x_u ? a1 : z1;
+      g.wait_id = c1;
+      g.signal_id = k;
+      g.count = 0;
+      g.after = c1;
+      if (!x_live || g.u1 <= g.u0 || g.v1 <= g.v0) empty_ids[nempty++] = k;
+    }
+    sx.wait_n = 1;
+    sx.wait_base = ws.flags;
+    sx.wait_off[0] = WS_FLAG_LOCAL0;
+    sx.wait_epoch[0] = le;
+    // Z: piece k = a-range k, everything along its other pencil dimension
+    p3dfftcu_sync sz;
+    memset(&sz, 0, sizeof sz);
+    sz.ngroups = K;
+    sz.ctl = (char *)pl->ctl + 8 * 64;
+    const bool z_u = a == Z.u;
+    for (int k = 0; k < K; k++) {
+      p3dfftcu_group &g = sz.grp[k];
+      const int a0 = X.tri_a_range[k].first, a1 = X.tri_a_range[k].second;
+      g.u0 = z_u ? a0 : 0;
+      g.u1 = z_u ? a1 : (int)Z.desc.nu;
+      g.v0 = z_u ? 0 : a0;
+      g.v1 = z_u ? (int)Z.desc.nv : a1;
+      g.wait_id = k;
+      g.signal_id = -1;
+    }
+    sx.sig_n = sz.wait_n = np;
+    sz.wait_base = ws.flags;
+    for (int q = 0; q < np; q++) {
+      const int wr = peer_wr(pl, X, q);
+      const unsigned long long e = ++ws.epoch_with[wr];
+      sx.sig_ptr[q] = (char *)ws.peers[wr].flags + 8 * (WS_FLAG_GROUP0 + ws.world_rank * WS_FLAGS_PER_SRC);
+      sx.sig_epoch[q] = e;
+      sz.wait_off[q] = WS_FLAG_GROUP0 + wr * WS_FLAGS_PER_SRC;
+      sz.wait_epoch[q] = e;
+    }
+    const bool z_live = Z.pair_handle && p3dfftcu_stage_sync_capable(Z.pair_handle);
+    void *d1[1] = {ws.buf[s & 1]}, *dz[1] = {zdst};
+    if (l_live) GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ssrc, d1, 1, gL, stream, lcap, &sl), pl, "stage launch");
+    if (nempty) GPU(p3dfftcu_flags_publish(sx.sig_ptr, sx.sig_epoch, np, empty_ids, nempty, xstream), pl, "flag publish");
+    if (x_live) GPU(p3dfftcu_stage_exec_sync(X.pair_handle, ws.buf[s & 1], xdsts, np, gX, xstream, xcap, &sx), pl, "stage launch");
+    if (z_live) {
+      GPU(p3dfftcu_stage_exec_sync(Z.pair_handle, ws.buf[w], dz, 1, deriv_g[2], stream, lcap, &sz), pl, "stage launch");
+      if (p3dfftcu_stage_sync_capable(Z.pair_handle) == 2)  // the SMs the exchange kernel leaves join Z's work pool
+        GPU(p3dfftcu_stage_exec_sync(Z.pair_handle, ws.buf[w], dz, 1, deriv_g[2], xstream, xcap, &sz), pl, "stage launch");
+    }
+  } else if (l_first) {
     // L publishes chunk c in this GPU's flag array, X waits for it
     const unsigned long long le = ++ws.local_epoch;
     for (size_t c = 0; c < C; c++) {
       sl.grp[c].signal_id = (int)c;
       sx.grp[c].wait_id = (int)c;
     }
+    sl.boost_ctas = sms;  // the first chunk on every SM: nothing else can run before it is complete
+    sl.boost_groups = 1;
     sl.sig_n = 1;
     sl.sig_ptr[0] = (char *)ws.flags + 8 * WS_FLAG_LOCAL0;
     sl.sig_epoch[0] = le;
@@ -526,9 +615,16 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
       const size_t ls = l_first ? s : s + 1;
       void *ldst = ls + 1 == S ? dst : ws.buf[ls & 1];
       if (l_first || (const void *)ldst != ssrc) {  // (in-place call whose output would overwrite X's input: run in sequence)
-        const int dg[2] = {deriv_len(s), deriv_len(s + 1)};
-        if (st.pair_sync) run_pair_sync(pl, s, ssrc, ldst, dg, stream);
+        const bool triple = l_first && st.pair_sync && pl->stages[s + 1].triple && s + 3 == S;
+        const int dg[3] = {deriv_len(s), deriv_len(s + 1), triple ? deriv_len(s + 2) : 0};
+        if (st.pair_sync) run_pair_sync(pl, s, ssrc, ldst, dg, stream, triple ? dst : nullptr);
         else run_pair(pl, s, ssrc, ldst, dg, stream);
+        if (triple) {  // the whole triple is booked on its first stage
+          if (timing)
+            for (size_t e = s + 1; e <= s + 3; e++) GPU(p3dfftcu_event_record(ev[ev0 + e], stream), pl, "event");
+          s += 2;
+          continue;
+        }
         if (l_first && s + 2 == S)  // the exchange stage is the plan's last: its result sits in my work buffer
           GPU(p3dfftcu_memcpy(dst, ws.buf[(s + 1) & 1], (size_t)pl->stages[s + 1].out_bytes, 2, stream), pl, "device copy");
         if (timing) {  // the pair is timed as a whole: its duration is booked on the first stage, zero on the second

@@ -65,7 +65,15 @@ struct StagePlan {
   std::vector<std::pair<int, int> > chunk_range;  // [c0, c1) of every chunk along chunk_dim on this rank
   p3dfftcu_stage pair_handle;                     // the whole stage planned with CTAs that fill an SM
   bool pair_sync;                                 // (on both stages) agreed by all ranks at plan time
-  StagePlan() : handle(nullptr), pair(PAIR_NONE), chunk_dim(-1), pair_handle(nullptr), pair_sync(false) {}
+  // local stage L -> exchange stage X -> local stage Z as THREE persistent kernels (set on X; forward slab plans): the
+  // first tri_c1 chunks of X follow L chunk by chunk; the rest of the chunk dimension is then cut along L's transform
+  // dimension instead (tri_a_range), X publishes each of those pieces to the peers and Z -- which transforms the gathered
+  // dimension and needs every sender's share of a piece, nothing else -- runs on it while X is still sending the next
+  bool triple;
+  int tri_c1;
+  std::vector<std::pair<int, int> > tri_a_range;  // [a0, a1) along L.dim on this rank
+  StagePlan()
+      : handle(nullptr), pair(PAIR_NONE), chunk_dim(-1), pair_handle(nullptr), pair_sync(false), triple(false), tri_c1(0) {}
 };
 
 struct Plan {

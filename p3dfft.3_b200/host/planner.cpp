@@ -457,11 +457,46 @@ bool plan_overlap(Plan *pl, const std::vector<ProtoStage> &protos) {
         if (!make_chunk(X, pl->prec, cdim, c0, c1, &X.chunks[c], &pl->error)) return false;
       }
     used[x] = used[l] = true;
+    // L -> X -> Z triple (see plan.h): the stage after X transforms the dimension X gathers, as the plan's last stage
+    if (L.pair_sync && mode == StagePlan::PAIR_L_THEN_X && x + 2 == S && env_int("P3DFFT_B200_TRIPLE", 1)) {
+      StagePlan &Z = pl->stages[x + 1];
+      const int a = L.dim;
+      bool tri_ok = !Z.exchange && Z.kind != P3DFFTCU_K_EMPTY && Z.dim == X.xdim_gather && Z.dim == cdim && C >= 4;
+      if (tri_ok) {
+        p3dfftcu_stage_desc d = Z.desc;
+        d.whole_sm_ctas = 1;
+        if (p3dfftcu_stage_create(&d, &Z.pair_handle)) {
+          pl->error = std::string("pair stage setup failed: ") + p3dfftcu_last_error();
+          return false;
+        }
+        const bool empty = d.nu <= 0 || d.nv <= 0 || d.n_in <= 0;
+        if (!empty && !p3dfftcu_stage_sync_capable(Z.pair_handle)) tri_ok = false;
+      }
+      int t_l = tri_ok ? 1 : 0, t_g = t_l;
+      MPI_Allreduce(&t_l, &t_g, 1, MPI_INT, MPI_MIN, pl->comm);
+      if (t_g) {
+        // second phase = the last chunks, about `frac` of the chunk dimension; cut along a into K pieces (multiples of 16)
+        const int frac_pct = std::min(90, std::max(10, env_int("P3DFFT_B200_TRIPLE_PCT", 50)));
+        int c1 = C;
+        while (c1 > 1 && (bnd[C] - bnd[c1 - 1]) * 100 <= (long long)bnd[C] * frac_pct) c1--;
+        const int K = std::min(std::max(2, env_int("P3DFFT_B200_TRIPLE_PIECES", 4)), 8);
+        const int rep_a = px.rep_in[a], mine_a = X.in.ldims[a];
+        int ka = (rep_a + K - 1) / K;
+        ka = (ka + 15) / 16 * 16;
+        const int Ka = (rep_a + ka - 1) / ka;
+        if (c1 >= 1 && c1 < C && Ka >= 2 && c1 + 1 + Ka <= P3DFFTCU_MAXGRP) {
+          X.triple = true;
+          X.tri_c1 = c1;
+          for (int k = 0; k < Ka; k++) X.tri_a_range.push_back(std::make_pair(std::min(k * ka, mine_a), std::min((k + 1) * ka, mine_a)));
+          used[x + 1] = true;
+        }
+      }
+    }
   }
   bool any = false;
   for (size_t s = 0; s < S; s++) any = any || pl->stages[s].pair != StagePlan::PAIR_NONE;
   if (any) {
-    if (p3dfftcu_malloc(&pl->ctl, 8 * 64)) {
+    if (p3dfftcu_malloc(&pl->ctl, 8 * 96)) {
       pl->error = std::string("pair control block: ") + p3dfftcu_last_error();
       return false;
     }
@@ -755,6 +790,7 @@ std::string describe(const Plan &p) {
     o << ",\"pair\":" << st.pair << ",\"chunk_dim\":" << st.chunk_dim << ",\"chunks\":" << st.chunks.size()
       << ",\"pair_sync\":" << (st.pair_sync ? "true" : "false");
     if (st.pair_handle) o << ",\"pair_variant\":\"" << p3dfftcu_stage_variant(st.pair_handle) << "\"";
+    if (st.triple) o << ",\"triple\":true,\"tri_c1\":" << st.tri_c1 << ",\"tri_pieces\":" << st.tri_a_range.size();
     o << ",\"variant\":\"" << (st.handle ? p3dfftcu_stage_variant(st.handle) : "") << "\",\"segs\":[";
     for (int q = 0; q < st.desc.nseg; q++) {
       const p3dfftcu_seg &g = st.desc.seg[q];

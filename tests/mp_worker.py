@@ -53,6 +53,8 @@ def main():
         assert desc["ok"], desc
         if os.environ.get("P3DFFT_TEST_EXPECT_PAIRS") and c.get("expect_pairs", True):
             assert any(s["pair"] for s in desc["stages"]), ("no overlapped pair planned", desc)
+        if os.environ.get("P3DFFT_TEST_EXPECT_TRIPLE") and c.get("expect_triple", False):  # L -> X -> Z as three persistent kernels
+            assert any(s.get("triple") for s in desc["stages"]), ("no L-X-Z triple planned", desc)
         if os.environ.get("P3DFFT_TEST_EXPECT_SYNC") and c.get("expect_sync", True):  # persistent pair kernels with tile-group flags
             assert any(s["pair_sync"] for s in desc["stages"]), ("pair without the tile-group form", desc)
         og1 = orc.OGrid(g1d, c["dmap1"], c["mo1"], pd, rank, c.get("cs1", -1))

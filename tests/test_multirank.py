@@ -168,17 +168,22 @@ def test_overlapped_exchange_pairs():
     launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2])], env_extra={"P3DFFT_B200_OVERLAP": "0"})
 
 
-SYNC_PAIRS = {"P3DFFT_TEST_EXPECT_PAIRS": "1", "P3DFFT_TEST_EXPECT_SYNC": "1"}
+SYNC_PAIRS = {"P3DFFT_TEST_EXPECT_PAIRS": "1", "P3DFFT_TEST_EXPECT_SYNC": "1", "P3DFFT_TEST_EXPECT_TRIPLE": "1"}
 
 
 def test_persistent_pair_kernels_with_flags():
     """overlapped pairs as ONE persistent launch per stage: the chunks are tile groups, "chunk complete" is a flag word written
     inside the producing kernel (local stage -> exchange stage on this rank; exchange stage -> every peer's local stage) and
     awaited inside the consuming one.  Slab forward (L then X) and backward (X then L), uneven blocks over 3 ranks, pencil
-    grid, fused derivative in either member, in-place"""
+    grid, fused derivative in either member, in-place.  Forward slab plans run as a TRIPLE (asserted): local stage -> exchange
+    stage -> last local stage as three persistent kernels, the exchange stage publishing the second half of its work piece by
+    piece to the peers' last stages"""
     n = (128, 64, 64)
-    launch(2, [fwd(n, [1, 1, 2]), bwd(n, [1, 1, 2]), fwd(n, [1, 1, 2], deriv=1), fwd(n, [1, 1, 2], deriv=0),
-               c2c((64, 64, 64), [1, 1, 2], inplace=True)], env_extra=SYNC_PAIRS, timeout=1500)
+    T = dict(expect_triple=True)
+    launch(2, [fwd(n, [1, 1, 2], **T), bwd(n, [1, 1, 2]), fwd(n, [1, 1, 2], deriv=1, **T), fwd(n, [1, 1, 2], deriv=0, **T),
+               fwd(n, [1, 1, 2], deriv=2, **T), c2c((64, 64, 64), [1, 1, 2], inplace=True, **T)], env_extra=SYNC_PAIRS, timeout=1500)
+    launch(4, [fwd((128, 64, 128), [1, 1, 4], reps=1, **T)], env_extra=SYNC_PAIRS, timeout=1500)
+    launch(2, [fwd(n, [1, 1, 2], reps=1)], env_extra={"P3DFFT_B200_TRIPLE": "0", "P3DFFT_TEST_EXPECT_SYNC": "1"}, timeout=1500)
     small = dict(SYNC_PAIRS, P3DFFT_B200_OVERLAP_ALIGN="1", P3DFFT_B200_OVERLAP_CHUNKS="3")
     launch(3, [fwd((128, 64, 20), [1, 1, 3], reps=2), bwd((128, 64, 64), [1, 1, 3], reps=2)], env_extra=small, timeout=1500)
     launch(4, [fwd((128, 64, 64), [1, 2, 2], reps=1), bwd((128, 64, 64), [1, 2, 2], reps=1)], env_extra=small, timeout=1500)
@@ -225,8 +230,11 @@ def test_gpu_overlapped_pairs_parity(nranks):
         pytest.skip("needs a GPU")
     n = (256, 128, 32 * nranks)
     pd = [1, 1, nranks]
-    cs = [fwd(n, pd), bwd(n, pd), fwd(n, pd, types=RCC_S), fwd(n, pd, deriv=1), fwd(n, pd, deriv=0), c2c((128, 128, 32 * nranks), pd)]
+    T = dict(expect_triple=True)  # forward slab plans: L -> X -> Z as three persistent kernels
+    cs = [fwd(n, pd, **T), bwd(n, pd), fwd(n, pd, types=RCC_S, **T), fwd(n, pd, deriv=1, **T), fwd(n, pd, deriv=0, **T),
+          fwd(n, pd, deriv=2, **T), c2c((128, 128, 32 * nranks), pd, **T), c2c((128, 128, 32 * nranks), pd, inplace=True, **T)]
     launch(nranks, cs, mode="gpu", timeout=1200, env_extra=SYNC_PAIRS)
+    launch(nranks, cs[:2], mode="gpu", timeout=1200, env_extra={"P3DFFT_B200_TRIPLE": "0", "P3DFFT_TEST_EXPECT_SYNC": "1"})
     launch(nranks, cs[:2], mode="gpu", timeout=1200, env_extra={"P3DFFT_B200_PAIR_SYNC": "0", "P3DFFT_TEST_EXPECT_PAIRS": "1"})
     if nranks >= 4:
         pp = [1, 2, nranks // 2]
@@ -240,7 +248,7 @@ def test_gpu_overlapped_pairs_512x512x256():
     if _ngpu() < 1:
         pytest.skip("needs a GPU")
     n = (512, 512, 256)
-    launch(4, [fwd(n, [1, 1, 4], reps=2), bwd(n, [1, 1, 4], reps=2)], mode="gpu", timeout=1500, env_extra=SYNC_PAIRS)
+    launch(4, [fwd(n, [1, 1, 4], reps=2, expect_triple=True), bwd(n, [1, 1, 4], reps=2)], mode="gpu", timeout=1500, env_extra=SYNC_PAIRS)
 
 
 @pytest.mark.parametrize("switch", ["P3DFFT_B200_NO_PAD", "P3DFFT_B200_NO_PIPE", "P3DFFT_B200_NO_FASTCORE", "P3DFFT_B200_FORCE_GENERIC"])
