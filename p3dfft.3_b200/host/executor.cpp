@@ -232,9 +232,11 @@ static void pair_caps(int npeers, int *xcap, int *lcap) {
     int v = e ? atoi(e) : 0;
     return v > 0 ? v : 0;
   }();
-  // measured (1024^3 double): 2 GPUs 74 of 148 SMs best (the local stage is half as long as the exchange); 4 and 8 GPUs,
-  // where the local stage is a third or less of the exchange, ~90-100
-  int x = xs > 0 ? xs : (npeers <= 2 ? sms / 2 : sms * 5 / 8);
+  // measured (1024^3 double, persistent pair kernels, profiles/r02_pairs_*): half of the SMs is best on 2, 4 and 8 GPUs
+  // (8 GPUs: 56 / 74 / 92 SMs -> 4.06 / 3.87 / 3.91 ms per round trip; all-to-all stores alone reach 636 GB/s from 74 CTAs
+  // and 669 GB/s from 148, tools/microbench/a2a_bench.cu)
+  (void)npeers;
+  int x = xs > 0 ? xs : sms / 2;
   if (x >= sms) x = sms - 1;
   if (x < 1) x = 1;
   *xcap = x;        // the chunk stages of a pair are planned with CTAs that fill an SM (whole_sm_ctas): one CTA per SM,
@@ -387,6 +389,21 @@ static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, cons
   sx.ctl = (char *)pl->ctl + 8 * 32;
   GPU(p3dfftcu_memset(pl->ctl, 0, 8 * 96, stream), pl, "memset");
   static const int sms = p3dfftcu_num_sms();
+  // P3DFFT_B200_OVERLAP_TRACE=1: when each kernel of the pair ended, relative to the fork (rank 0)
+  static const bool trace = getenv("P3DFFT_B200_OVERLAP_TRACE") && atoi(getenv("P3DFFT_B200_OVERLAP_TRACE"));
+  static std::vector<void *> tev;
+  const char *tname[8];
+  int ntr = 0;
+  auto mark = [&](const char *name, void *st) {
+    if (!trace || ntr >= 8) return;
+    while ((int)tev.size() <= ntr) {
+      void *e = nullptr;
+      GPU(p3dfftcu_event_create(&e), pl, "event");
+      tev.push_back(e);
+    }
+    tname[ntr] = name;
+    GPU(p3dfftcu_event_record(tev[ntr++], st), pl, "event");
+  };
   GPU(p3dfftcu_event_record(ev[0], stream), pl, "event");
   GPU(p3dfftcu_stream_wait_event(xstream, ev[0]), pl, "stream wait");
   peer_barrier(pl, X, xstream);  // every peer has finished reading its buffer w
@@ -470,12 +487,17 @@ static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, cons
     const bool z_live = Z.pair_handle && p3dfftcu_stage_sync_capable(Z.pair_handle);
     void *d1[1] = {ws.buf[s & 1]}, *dz[1] = {zdst};
     if (l_live) GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ssrc, d1, 1, gL, stream, lcap, &sl), pl, "stage launch");
+    mark("L", stream);
+    mark("barrier", xstream);
     if (nempty) GPU(p3dfftcu_flags_publish(sx.sig_ptr, sx.sig_epoch, np, empty_ids, nempty, xstream), pl, "flag publish");
     if (x_live) GPU(p3dfftcu_stage_exec_sync(X.pair_handle, ws.buf[s & 1], xdsts, np, gX, xstream, xcap, &sx), pl, "stage launch");
+    mark("X", xstream);
     if (z_live) {
       GPU(p3dfftcu_stage_exec_sync(Z.pair_handle, ws.buf[w], dz, 1, deriv_g[2], stream, lcap, &sz), pl, "stage launch");
+      mark("Za", stream);
       if (p3dfftcu_stage_sync_capable(Z.pair_handle) == 2)  // the SMs the exchange kernel leaves join Z's work pool
         GPU(p3dfftcu_stage_exec_sync(Z.pair_handle, ws.buf[w], dz, 1, deriv_g[2], xstream, xcap, &sz), pl, "stage launch");
+      mark("Zb", xstream);
     }
   } else if (l_first) {
     // L publishes chunk c in this GPU's flag array, X waits for it
@@ -495,8 +517,12 @@ static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, cons
     sx.wait_epoch[0] = le;
     void *d1[1] = {ws.buf[s & 1]};
     if (l_live) GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ssrc, d1, 1, gL, stream, lcap, &sl), pl, "stage launch");
+    mark("L", stream);
+    mark("barrier", xstream);
     if (x_live) GPU(p3dfftcu_stage_exec_sync(X.pair_handle, ws.buf[s & 1], xdsts, np, gX, xstream, xcap, &sx), pl, "stage launch");
+    mark("X", xstream);
     peer_barrier(pl, X, xstream);  // every peer's blocks have landed in my buffer w
+    mark("end barrier", xstream);
   } else {
     // X publishes chunk c in every peer's flag array (row = my world rank), L waits for chunk c of every peer
     int empty_ids[P3DFFTCU_MAXGRP], nempty = 0;
@@ -516,18 +542,35 @@ static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, cons
       sl.wait_off[q] = WS_FLAG_GROUP0 + wr * WS_FLAGS_PER_SRC;
       sl.wait_epoch[q] = e;
     }
+    mark("barrier", xstream);
     if (nempty) GPU(p3dfftcu_flags_publish(sx.sig_ptr, sx.sig_epoch, np, empty_ids, nempty, xstream), pl, "flag publish");
     if (x_live) GPU(p3dfftcu_stage_exec_sync(X.pair_handle, ssrc, xdsts, np, gX, xstream, xcap, &sx), pl, "stage launch");
+    mark("X", xstream);
     void *d1[1] = {ldst};
     if (l_live) {
       GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ws.buf[w], d1, 1, gL, stream, lcap, &sl), pl, "stage launch");
+      mark("La", stream);
       // the SMs the exchange kernel leaves join the local stage (same tile counter) when its kernel hands tiles out dynamically
       if (p3dfftcu_stage_sync_capable(L.pair_handle) == 2)
         GPU(p3dfftcu_stage_exec_sync(L.pair_handle, ws.buf[w], d1, 1, gL, xstream, xcap, &sl), pl, "stage launch");
+      mark("Lb", xstream);
     }
   }
   GPU(p3dfftcu_event_record(ev[1], xstream), pl, "event");
   GPU(p3dfftcu_stream_wait_event(stream, ev[1]), pl, "stream wait");
+  if (trace) {
+    GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");
+    if (pl->rank == 0) {
+      fprintf(stderr, "pair-sync trace (%s%s, xcap %d lcap %d), kernel end times in ms since the fork:", l_first ? "L first" : "X first",
+              (l_first && X.triple && zdst) ? ", triple" : "", xcap, lcap);
+      for (int i = 0; i < ntr; i++) {
+        float t = 0;
+        GPU(p3dfftcu_event_elapsed(ev[0], tev[i], &t), pl, "event");
+        fprintf(stderr, "  %s %.3f", tname[i], t);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
 }
 
 static void add_timer(const StagePlan &st, bool deriv, double sec) {

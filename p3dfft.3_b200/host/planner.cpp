@@ -476,9 +476,26 @@ bool plan_overlap(Plan *pl, const std::vector<ProtoStage> &protos) {
       MPI_Allreduce(&t_l, &t_g, 1, MPI_INT, MPI_MIN, pl->comm);
       if (t_g) {
         // second phase = the last chunks, about `frac` of the chunk dimension; cut along a into K pieces (multiples of 16)
-        const int frac_pct = std::min(90, std::max(10, env_int("P3DFFT_B200_TRIPLE_PCT", 50)));
+        // the second phase cannot start before L is complete: the first phase has to last as long as L does on its half
+        // of the SMs (~37 GB/s per SM) while X sends at ~630 GB/s (measured, profiles/r02_pairs_4gpu_trace.txt)
+        int pct = 50;
+        {
+          double lb = 1, xb = 0;
+          for (int i = 0; i < 3; i++) lb *= protos[l].rep_in[i];
+          lb = lb * protos[l].dt_in * pl->prec;
+          double ob = 1;
+          for (int i = 0; i < 3; i++) ob *= protos[l].rep_out[i];
+          lb += ob * protos[l].dt_out * pl->prec;
+          const int np = pl->pgrid->ProcDims[px.comm_dim];
+          xb = ob * protos[l].dt_out * pl->prec * (np - 1) / np;
+          const double t_l = lb / (74 * 36.8e9), t_x = xb / 630e9;
+          const double f1 = std::min(0.8, std::max(0.5, t_x > 0 ? t_l / t_x : 0.5));
+          pct = (int)(100 * (1 - f1) + 0.5);
+        }
+        const int frac_pct = std::min(90, std::max(10, env_int("P3DFFT_B200_TRIPLE_PCT", pct)));
         int c1 = C;
         while (c1 > 1 && (bnd[C] - bnd[c1 - 1]) * 100 <= (long long)bnd[C] * frac_pct) c1--;
+        if (c1 == C) c1 = C - 1;  // (at least the last chunk)
         const int K = std::min(std::max(2, env_int("P3DFFT_B200_TRIPLE_PIECES", 4)), 8);
         const int rep_a = px.rep_in[a], mine_a = X.in.ldims[a];
         int ka = (rep_a + K - 1) / K;

@@ -13,6 +13,7 @@ for SY in ${SYNCS:-1 0}; do
     if [ "$XS" = default ]; then unset P3DFFT_B200_OVERLAP_XSMS; else export P3DFFT_B200_OVERLAP_XSMS=$XS; fi
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
        bench.py --gpus $N --no-cpu --no-e2e --steps ${STEPS:-10} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/r02_pairs_${N}_sync${SY}_$XS.json 2> gpurun_out/r02_pairs_${N}_sync${SY}_$XS.err
+    grep "pair-sync trace" gpurun_out/r02_pairs_${N}_sync${SY}_$XS.err | tail -2 | cut -c1-400 | tee -a gpurun_out/r02_pairs_$N.txt
     python - $N $SY $XS <<'PY' | tee -a gpurun_out/r02_pairs_$N.txt
 import json, sys
 n, sy, xs = sys.argv[1:4]
