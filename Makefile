@@ -28,8 +28,8 @@ $(OBJDIR)/gpu_layer.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) in
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-# pipelined pow2 kernels: one object per (precision, kind)
-PIPEKEYS := 4_1 4_2 4_3 4_4 8_1 8_2 8_3 8_4
+# pipelined pow2 kernels: one object per (precision, kind); kind 5 = every r2r kind (DCT/DST I-IV)
+PIPEKEYS := 4_1 4_2 4_3 4_4 4_5 8_1 8_2 8_3 8_4 8_5
 PIPEOBJ  := $(PIPEKEYS:%=$(OBJDIR)/pipe_%.o)
 $(OBJDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
 	@mkdir -p $(OBJDIR)

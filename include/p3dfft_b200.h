@@ -42,6 +42,14 @@ void p3dfft_b200_enable_timers(int on);
 int p3dfft_b200_stage_times(int plan, float *ms, int max_stages);
 /* 1 if a usable CUDA device was found at p3dfft_setup() (plans can be built and inspected without one) */
 int p3dfft_b200_have_device(void);
+/* How host arrays passed to exec calls cross PCIe (also the environment variable P3DFFT_B200_HOST_STAGING):
+ *   "ring" (default)  through a ring of pinned chunks, CPU copy on P3DFFT_B200_HOST_THREADS (4) threads overlapped with the DMA
+ *   "register"        page-lock the array on first use (cudaHostRegister) and remember the range: full link rate from the second
+ *                     call on; the application must call p3dfft_b200_host_release(ptr) before it frees such an array
+ *   "plain"           a bare cudaMemcpyAsync
+ * Arrays the application page-locked itself always take the direct asynchronous copy. */
+void p3dfft_b200_set_host_staging(const char *mode);
+void p3dfft_b200_host_release(const void *ptr);
 
 /* ---------------------------------------------------------------- thin GPU layer */
 enum {
@@ -103,6 +111,20 @@ int p3dfftcu_memcpy(void *dst, const void *src, size_t bytes, int kind, void *st
 int p3dfftcu_stream_sync(void *stream);
 /* 1 device memory, 0 host memory (pageable or pinned), <0 error */
 int p3dfftcu_pointer_is_device(const void *ptr);
+/* ---- host arrays of exec calls (reference semantics: `in` / `out` are ordinary heap arrays, sample/C++/test3D_r2c.C:197-205).
+ * 1 if ptr is page-locked host memory (cudaHostAlloc / cudaHostRegister, by anybody), 0 if pageable */
+int p3dfftcu_host_is_pinned(const void *ptr);
+/* "register" mode: page-lock the user's array (cudaHostRegister) and remember the range, so later execs on the same array
+ * copy at the pinned rate.  Returns 0 when [ptr, ptr+bytes) is page-locked now (by this call, an earlier one, or the
+ * application), non-zero when it could not be locked (the caller then uses p3dfftcu_memcpy_staged).  Ranges are released by
+ * p3dfftcu_host_unpin / _unpin_all, or evicted least-recently-used beyond 32 ranges / P3DFFT_B200_HOST_PIN_MAX_GB (64). */
+int p3dfftcu_host_pin(const void *ptr, size_t bytes);
+/* release the registration of the range that contains ptr (p3dfft_b200_host_release) */
+int p3dfftcu_host_unpin(const void *ptr);
+int p3dfftcu_host_unpin_all(void);
+/* host <-> device copy of a PAGEABLE array through a double-buffered ring of pinned chunks (the CPU copy of chunk c+1
+ * overlaps the DMA of chunk c); kind 0 host->device, 1 device->host; returns when the copy is complete */
+int p3dfftcu_memcpy_staged(void *dst, const void *src, size_t bytes, int kind, void *stream);
 
 int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out);
 int p3dfftcu_stage_destroy(p3dfftcu_stage st);

@@ -65,6 +65,7 @@ struct StageParams {
   const void *tw_core;  // fastcore kernel: exp(-2 pi i j / M) of the power-of-two core
   const void *chirp;    // Bluestein: c_j = exp(-i pi j^2 / L), j < L
   const void *bhat;     // Bluestein: FFT_M of the wrapped conj chirp, divided by M
+  int pipe_bytes;   // TMA kernel, r2r kinds: bytes of one pencil's bulk copy (n_in elements rounded up to 16 bytes)
   int deriv_g;      // > 0: spectral derivative epilogue with full length g
   int nseg;
   SegDev seg[P3DFFTCU_MAXSEG];

@@ -6,6 +6,8 @@
 
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,21 +27,24 @@ using namespace p3b;
 
 namespace p3b {
 #define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int ts, int M, int P);
-P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4)
-P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4)
+P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4) P3B_DECL_PIPE(4, 5)
+P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4) P3B_DECL_PIPE(8, 5)
 #undef P3B_DECL_PIPE
 const PipeInfo *pipe_lookup(int prec, int kind, int ts, int M, int P) {
+  if (kind >= P3DFFTCU_K_DCT1) kind = kPipeR2R;  // one kernel family for all r2r kinds
   if (prec == 4) switch (kind) {
       case 1: return pipe_lookup_p4_1(ts, M, P);
       case 2: return pipe_lookup_p4_2(ts, M, P);
       case 3: return pipe_lookup_p4_3(ts, M, P);
       case 4: return pipe_lookup_p4_4(ts, M, P);
+      case 5: return pipe_lookup_p4_5(ts, M, P);
     }
   if (prec == 8) switch (kind) {
       case 1: return pipe_lookup_p8_1(ts, M, P);
       case 2: return pipe_lookup_p8_2(ts, M, P);
       case 3: return pipe_lookup_p8_3(ts, M, P);
       case 4: return pipe_lookup_p8_4(ts, M, P);
+      case 5: return pipe_lookup_p8_5(ts, M, P);
     }
   return nullptr;
 }
@@ -262,6 +267,7 @@ struct PipePlan {
   int tile_u = 1, tile_v = 1, tu_log2 = 0, load_ord = 0, store_ord = 0;
   long long tiles_u = 0, tiles_v = 0, ntiles = 0;
   int vfast = 0;
+  int bytes = 0;  // r2r kinds: bytes of one pencil's bulk copy
 };
 
 struct FastPlan {
@@ -276,6 +282,7 @@ struct p3dfftcu_stage_s {
   p3dfftcu_stage_desc d;
   StageParams P;
   Variant variant;
+  Variant fallback = V_GENERIC;  // V_PIPE only: the variant that takes inputs a bulk copy cannot (pointer not 16-byte aligned)
   int threads;
   int grid;
   size_t smem;
@@ -452,23 +459,36 @@ int fast_setup(p3dfftcu_stage_s *st) {
 
 // picks the pipelined kernel (pow2_pipe.cuh) for a stage; returns 0 ok, <0 not applicable, >0 CUDA error
 int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
-  if (!pow2_supported(d)) return -1;
+  const bool r2r = d.kind >= P3DFFTCU_K_DCT1;
   const bool real = d.kind == P3DFFTCU_K_R2C || d.kind == P3DFFTCU_K_C2R;
-  const int M = real ? d.nfft / 2 : d.nfft;
+  int M;
+  if (r2r) {  // the kind's symmetric extension has a power-of-two length: DCT-I of 2^k+1 points, DST-I of 2^k-1, II-IV of 2^k
+    M = internal_length(d.kind, d.nfft);
+    if (M < 64 || M > 4096 || (M & (M - 1))) return -1;
+  } else {
+    if (!pow2_supported(d)) return -1;
+    M = real ? d.nfft / 2 : d.nfft;
+  }
   int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
   int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
   if (fin != 0 || d.is_d != 1) return -1;  // bulk copies move whole pencils: the transform dimension must be unit-stride
   // 16-byte aligned pencils of a multiple of 16 bytes.  esz = bytes of one input element
   const long long esz = (long long)d.prec * d.dt_in;
   if ((d.is_u * esz) % 16 || (d.is_v * esz) % 16) return -1;
-  if (((long long)d.n_in * esz) % 16) {
-    // single-precision C2R (M+1 elements of 8 bytes): the copy takes one element more, which must belong to the array:
-    // true when the rows are padded (library-owned intermediates, planner.cpp) so that every pencil is followed by a gap
-    const bool roomy = (d.nu <= 1 || d.is_u > d.n_in) && (d.nv <= 1 || d.is_v > d.n_in);
-    if (!(d.kind == P3DFFTCU_K_C2R && d.prec == 4 && roomy)) return -1;
+  const long long pencil_bytes = (long long)d.n_in * esz, copy_bytes = (pencil_bytes + 15) / 16 * 16;
+  if (pencil_bytes % 16) {
+    // single-precision C2R (M+1 elements of 8 bytes), r2r pencils of 2^k+-1 values: the copy takes up to 15 bytes more, which
+    // must belong to the array: true when the rows are padded (library-owned intermediates, planner.cpp) so that every
+    // pencil is followed by a gap
+    long long pitch = 0;  // smallest stride between two pencils
+    if (d.nu > 1) pitch = d.is_u;
+    if (d.nv > 1 && (pitch == 0 || d.is_v < pitch)) pitch = d.is_v;
+    const bool roomy = pitch * esz >= copy_bytes;
+    if (!(((d.kind == P3DFFTCU_K_C2R && d.prec == 4) || r2r) && roomy)) return -1;
   }
+  pp->bytes = (int)copy_bytes;
   const int ts = fout != 0;
-  const size_t csz = (size_t)d.prec * 2;
+  const size_t csz = (size_t)d.prec * (r2r ? d.dt_out : 2);  // element size of the output runs
   const int E = pow2_values_per_thread(M), TP = M / E;
   // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
   int want = ts ? (int)(128 / csz) : (256 / TP > 0 ? 256 / TP : 1);
@@ -517,16 +537,16 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   pp->ntiles = pp->tiles_u * pp->tiles_v;
   pp->vfast = d.nv > 1 && (d.nu <= 1 || d.seg[0].os_v < d.seg[0].os_u);
   if (cudaFuncSetAttribute(info->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(info->func_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
+  if (info->func_sync && cudaFuncSetAttribute(info->func_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, info->func, info->threads, info->smem) != cudaSuccess) return 1;
   if (occ < 1) occ = 1;
   long long g = (long long)g_num_sms * occ;
   pp->grid = (int)(pp->ntiles < g ? (pp->ntiles > 0 ? pp->ntiles : 1) : g);
   char nm[220];
-  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s> threads=%d tile=%dx%d%s store=%d smem=%zu grid=%d occ=%d",
-           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", info->threads, tu, tv, pp->vfast ? " v-fast" : "", pp->store_ord, info->smem,
-           pp->grid, occ);
+  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s%s> threads=%d tile=%dx%d%s store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", r2r ? ",r2r" : "", info->threads, tu, tv,
+           pp->vfast ? " v-fast" : "", pp->store_ord, info->smem, pp->grid, occ);
   *name = nm;
   return 0;
 }
@@ -602,6 +622,254 @@ int p3dfftcu_pointer_is_device(const void *ptr) {
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
 
+// ---- page-locked user arrays (LRU cache of cudaHostRegister'ed ranges) and the staging ring for arrays that cannot be locked
+namespace {
+struct PinRange {
+  uintptr_t base;
+  size_t bytes;
+  unsigned long long used;
+};
+std::vector<PinRange> g_pins;
+unsigned long long g_pin_tick = 0;
+size_t pin_total() {
+  size_t t = 0;
+  for (const PinRange &r : g_pins) t += r.bytes;
+  return t;
+}
+void pin_drop(size_t i) {
+#ifndef P3B_EMU
+  cudaHostUnregister((void *)g_pins[i].base);
+  cudaGetLastError();
+#endif
+  g_pins.erase(g_pins.begin() + (long)i);
+}
+const size_t kRingChunk = (size_t)32 << 20;
+const int kRingSlots = 4;
+void *g_ring[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};
+cudaEvent_t g_ring_ev[kRingSlots];
+
+// CPU side of the staging ring: one memcpy split over a few threads (a single core copies ~10 GB/s, PCIe 5 x16 moves ~50)
+class CopyPool {
+ public:
+  explicit CopyPool(int n) {
+    for (int i = 1; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
+    parts_.resize((size_t)n);
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (std::thread &t : workers_) t.join();
+  }
+  void copy(void *dst, const void *src, size_t n) {
+    const size_t T = parts_.size();
+    if (T <= 1 || n < ((size_t)1 << 20)) {
+      memcpy(dst, src, n);
+      return;
+    }
+    const size_t per = ((n + T - 1) / T + 4095) / 4096 * 4096;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (size_t i = 0; i < T; i++) {
+        const size_t off = i * per < n ? i * per : n, len = off + per < n ? per : n - off;
+        parts_[i] = Part{(char *)dst + off, (const char *)src + off, len};
+      }
+      pending_ = (int)T - 1;
+      gen_++;
+    }
+    cv_.notify_all();
+    if (parts_[0].n) memcpy(parts_[0].dst, parts_[0].src, parts_[0].n);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  struct Part {
+    char *dst;
+    const char *src;
+    size_t n;
+  };
+  void loop(int i) {
+    unsigned long long seen = 0;
+    for (;;) {
+      Part p;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        p = parts_[(size_t)i];
+      }
+      if (p.n) memcpy(p.dst, p.src, p.n);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_--;
+      }
+      done_.notify_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<Part> parts_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  unsigned long long gen_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+CopyPool *g_pool = nullptr;
+CopyPool &copy_pool() {
+  if (!g_pool) {
+    const char *e = getenv("P3DFFT_B200_HOST_THREADS");
+    int n = e ? atoi(e) : 4;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && n > hw) n = hw;
+    if (n < 1) n = 1;
+    g_pool = new CopyPool(n);
+  }
+  return *g_pool;
+}
+}  // namespace
+
+int p3dfftcu_host_is_pinned(const void *ptr) {
+#ifdef P3B_EMU
+  (void)ptr;
+  return 1;
+#else
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return at.type == cudaMemoryTypeHost ? 1 : 0;
+#endif
+}
+
+int p3dfftcu_host_pin(const void *ptr, size_t bytes) {
+#ifdef P3B_EMU
+  (void)ptr; (void)bytes;
+  return 0;
+#else
+  if (!ptr || !bytes) return 0;
+  const uintptr_t a = (uintptr_t)ptr, e = a + bytes;
+  for (size_t i = 0; i < g_pins.size(); i++) {
+    PinRange &r = g_pins[i];
+    if (a >= r.base && e <= r.base + r.bytes) {  // known range
+      r.used = ++g_pin_tick;
+      return 0;
+    }
+  }
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) cudaGetLastError();
+  else if (at.type == cudaMemoryTypeHost) {
+    // page-locked by the application (cudaMallocHost / its own cudaHostRegister) -- unless it is one of OUR ranges that this
+    // request outgrows: then the range is re-registered at the new size below
+    bool ours = false;
+    for (size_t i = g_pins.size(); i-- > 0;)
+      if (a < g_pins[i].base + g_pins[i].bytes && e > g_pins[i].base) {
+        ours = true;
+        pin_drop(i);
+      }
+    if (!ours) return 0;
+  }
+  static const size_t cap = [] {
+    const char *v = getenv("P3DFFT_B200_HOST_PIN_MAX_GB");
+    const double gb = v ? atof(v) : 64.0;
+    return (size_t)(gb * 1073741824.0);
+  }();
+  if (bytes > cap) return 1;
+  for (size_t i = g_pins.size(); i-- > 0;)  // a stale overlapping range (the application re-allocated): drop it
+    if (a < g_pins[i].base + g_pins[i].bytes && e > g_pins[i].base) pin_drop(i);
+  while (!g_pins.empty() && (g_pins.size() >= 32 || pin_total() + bytes > cap)) {
+    size_t lru = 0;
+    for (size_t i = 1; i < g_pins.size(); i++)
+      if (g_pins[i].used < g_pins[lru].used) lru = i;
+    pin_drop(lru);
+  }
+  cudaError_t rc = cudaHostRegister((void *)ptr, bytes, cudaHostRegisterDefault);
+  if (rc != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  g_pins.push_back(PinRange{a, bytes, ++g_pin_tick});
+  return 0;
+#endif
+}
+
+int p3dfftcu_host_unpin(const void *ptr) {
+  const uintptr_t a = (uintptr_t)ptr;
+  for (size_t i = g_pins.size(); i-- > 0;)
+    if (a >= g_pins[i].base && a < g_pins[i].base + g_pins[i].bytes) pin_drop(i);
+  return 0;
+}
+
+int p3dfftcu_host_unpin_all(void) {
+  while (!g_pins.empty()) pin_drop(g_pins.size() - 1);
+#ifndef P3B_EMU
+  for (int i = 0; i < kRingSlots; i++)
+    if (g_ring[i]) {
+      cudaFreeHost(g_ring[i]);
+      cudaEventDestroy(g_ring_ev[i]);
+      g_ring[i] = nullptr;
+    }
+  delete g_pool;
+  g_pool = nullptr;
+#endif
+  return 0;
+}
+
+int p3dfftcu_memcpy_staged(void *dst, const void *src, size_t bytes, int kind, void *stream) {
+#ifdef P3B_EMU
+  return p3dfftcu_memcpy(dst, src, bytes, kind, stream) || p3dfftcu_stream_sync(stream);
+#else
+  cudaStream_t cs = (cudaStream_t)stream;
+  for (int i = 0; i < kRingSlots; i++)
+    if (!g_ring[i]) {
+      CK(cudaMallocHost(&g_ring[i], kRingChunk));
+      CK(cudaEventCreateWithFlags(&g_ring_ev[i], cudaEventDisableTiming));
+    }
+  CopyPool &pool = copy_pool();
+  const size_t nchunk = (bytes + kRingChunk - 1) / kRingChunk;
+  auto span = [&](size_t c, size_t *off, size_t *len) {
+    *off = c * kRingChunk;
+    *len = bytes - *off < kRingChunk ? bytes - *off : kRingChunk;
+  };
+  if (kind == 0) {  // host -> device: CPU copy into slot c % slots (once its previous DMA has drained), then DMA
+    for (size_t c = 0; c < nchunk; c++) {
+      size_t off, len;
+      span(c, &off, &len);
+      const int b = (int)(c % kRingSlots);
+      if (c >= (size_t)kRingSlots) CK(cudaEventSynchronize(g_ring_ev[b]));
+      pool.copy(g_ring[b], (const char *)src + off, len);
+      CK(cudaMemcpyAsync((char *)dst + off, g_ring[b], len, cudaMemcpyHostToDevice, cs));
+      CK(cudaEventRecord(g_ring_ev[b], cs));
+    }
+    CK(cudaStreamSynchronize(cs));
+  } else {  // device -> host: the DMAs of the next slots run while the CPU copies chunk c out of the ring
+    const size_t ahead = (size_t)kRingSlots - 1;
+    for (size_t c = 0; c < nchunk + ahead; c++) {
+      if (c < nchunk) {
+        size_t off, len;
+        span(c, &off, &len);
+        const int b = (int)(c % kRingSlots);
+        CK(cudaMemcpyAsync(g_ring[b], (const char *)src + off, len, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(g_ring_ev[b], cs));
+      }
+      if (c >= ahead) {
+        size_t off, len;
+        span(c - ahead, &off, &len);
+        const int b = (int)((c - ahead) % kRingSlots);
+        CK(cudaEventSynchronize(g_ring_ev[b]));
+        pool.copy((char *)dst + off, g_ring[b], len);
+      }
+    }
+  }
+  return 0;
+#endif
+}
+
 int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) {
   const p3dfftcu_stage_desc &d = *desc;
   if (d.prec != 4 && d.prec != 8) return failmsg("stage: prec must be 4 or 8");
@@ -672,6 +940,19 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) 
       }
     }
     if (!rc && st->variant == V_GENERIC) rc = d.prec == 8 ? setup_generic<double>(st) : setup_generic<float>(st);
+    // r2r kinds whose symmetric extension has a power-of-two length, unit-stride aligned pencils: the TMA-fed kernel; the
+    // variant chosen above stays as the fallback for input pointers a bulk copy cannot take
+    const char *nopipe = getenv("P3DFFT_B200_NO_PIPE"), *nor2r = getenv("P3DFFT_B200_NO_PIPE_R2R");
+    if (!rc && allow_fast && d.kind >= P3DFFTCU_K_DCT1 && !(nopipe && atoi(nopipe)) && !(nor2r && atoi(nor2r))) {
+      std::string pname;
+      int prc = pipe_setup(d, &st->pp, &pname);
+      if (prc > 0) rc = failmsg("pipelined stage kernel setup failed");
+      else if (prc == 0) {
+        st->fallback = st->variant;
+        st->variant = V_PIPE;
+        st->name = pname;
+      }
+    }
   }
   if (rc) {
     delete st;
@@ -709,7 +990,7 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
   Variant variant = st->variant;
   if (variant == V_PIPE) {
     // bulk copies need 16-byte aligned sources; an odd user pointer takes the non-pipelined kernel instead
-    if (((uintptr_t)in) % 16) variant = st->have_pw ? V_POW2 : V_GENERIC;
+    if (((uintptr_t)in) % 16) variant = st->have_pw ? V_POW2 : st->fallback;
   }
   if (variant == V_PIPE) {
     const PipePlan &pp = st->pp;
@@ -717,6 +998,7 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
       P.tile_u = pp.tile_u; P.tile_v = pp.tile_v; P.tu_log2 = pp.tu_log2;
       P.load_ord = pp.load_ord; P.store_ord = pp.store_ord;
       P.tiles_u = pp.tiles_u; P.tiles_v = pp.tiles_v; P.vfast = pp.vfast; P.ntiles = pp.ntiles;
+      P.pipe_bytes = pp.bytes;
       int grid = pp.grid;
       if (st->d.nseg > 1) {  // tuning: cap the CTAs of a fused exchange stage (NVLink-bound: may not need every SM)
         static const int xcap = getenv("P3DFFT_B200_XGRID") ? atoi(getenv("P3DFFT_B200_XGRID")) : 0;
@@ -750,7 +1032,7 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
 // 0: no tile-group form; 1: yes, tiles by CTA striding (all CTAs must be resident); 2: yes, tiles from a counter (launches that
 // share one control block share the work)
 int p3dfftcu_stage_sync_capable(p3dfftcu_stage st) {
-  if (st->empty || st->variant != V_PIPE || st->pp.ntiles <= 0) return 0;
+  if (st->empty || st->variant != V_PIPE || st->pp.ntiles <= 0 || !st->pp.info->launch_sync) return 0;
   if (st->pp.ld) return 2;  // transposed output: one CTA barrier per tile anyway, whole tiles are handed out
 #ifdef P3B_EMU
   return 1;  // (the emulation's group barriers are CTA barriers: thread groups cannot take different numbers of pencils)

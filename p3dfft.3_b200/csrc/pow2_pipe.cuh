@@ -164,6 +164,11 @@ template <typename C> __device__ __forceinline__ void st_out(C *p, C v) {
 
 constexpr size_t kPipeSmemMax = 232448 - 1024;  // 227 KB opt-in minus the static reserve
 
+// KIND of the kernel template: the P3DFFTCU_K_* value for C2C / R2C / C2R; kPipeR2R stands for EVERY r2r kind (DCT/DST I-IV,
+// real or complex data) whose internal FFT length L = M is a power of two -- which one is read from StageParams::kind at run
+// time (a CTA-uniform switch around the load and store loops; the M-point core in between is the same for all of them)
+constexpr int kPipeR2R = P3DFFTCU_K_DCT1;
+
 template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
   enum { E = Pow2Cfg<M>::E, TP = M / E, THREADS = P * TP, XP0 = Pow2Smem<M>::PENCIL };
   enum { R1 = Pow2Cfg<M>::R1, R2 = Pow2Cfg<M>::R2, R3 = Pow2Cfg<M>::R3 };
@@ -283,6 +288,107 @@ template <typename T, typename C> __device__ __forceinline__ C r2c_split(C zk, C
   return mk<T>((T)0.5 * (s.x + e.x), (T)0.5 * (s.y + e.y));
 }
 
+
+// ------------------------------------------------------------------ r2r kinds on the M-point core (KIND = kPipeR2R)
+// Every r2r kind is a complex-linear map: symmetric extension z of the n inputs to L = M points (with a half-sample
+// pre-twiddle for kinds III / IV), FFT_M, post-twiddle of the first n outputs (generic_stage.cuh has the same table, FFTW
+// definitions init.C:1191-1607) -- so the same code serves real data and the `_COMPLEX` variants (re and im separately,
+// init.C:1179-1188).  The pencil has landed in shared memory as it lies in global memory (n real or complex values);
+// v[m] = z[t + m TP] is built straight from it.
+template <typename T, int M, int E>
+__device__ __forceinline__ void r2r_load(typename cx<T>::type *v, const typename cx<T>::type *BA, int t, const StageParams &Q) {
+  typedef typename cx<T>::type C;
+  constexpr int TP = M / E;
+  const int n = Q.nfft;
+  const bool cplx = Q.dt_in == 2;
+  const T *BR = reinterpret_cast<const T *>(BA);
+  const C *__restrict__ tw2 = (const C *)Q.tw2;
+  const C zero = mk<T>((T)0, (T)0);
+  auto X = [&](int j) -> C { return cplx ? BA[j] : mk<T>(BR[j], (T)0); };
+  switch (Q.kind) {
+    case P3DFFTCU_K_DCT1:  // even extension, M = 2(n-1)
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        v[m] = X(i < n ? i : M - i);
+      }
+      break;
+    case P3DFFTCU_K_DST1:  // odd extension, M = 2(n+1): z_0 = z_{n+1} = 0
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        if (i == 0 || i == n + 1) v[m] = zero;
+        else v[m] = i <= n ? X(i - 1) : cneg(X(M - 1 - i));
+      }
+      break;
+    case P3DFFTCU_K_DCT2:  // half-sample even extension, M = 2n
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        v[m] = X(i < n ? i : M - 1 - i);
+      }
+      break;
+    case P3DFFTCU_K_DST2:  // half-sample odd extension
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        v[m] = i < n ? X(i) : cneg(X(M - 1 - i));
+      }
+      break;
+    case P3DFFTCU_K_DCT3:  // z_i = x_i w_i (i < n), 0 (i = n), -x_{2n-i} w_i (i > n); w = tw2
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        if (i == n) v[m] = zero;
+        else {
+          const C x = cmul(X(i < n ? i : M - i), __ldg(&tw2[i]));
+          v[m] = i < n ? x : cneg(x);
+        }
+      }
+      break;
+    case P3DFFTCU_K_DST3:  // z_0 = 0, z_i = i x_{i-1} w_i (i <= n), i x_{2n-i-1} w_i (i > n)
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        if (i == 0) v[m] = zero;
+        else v[m] = cmuli(cmul(X(i <= n ? i - 1 : M - i - 1), __ldg(&tw2[i])));
+      }
+      break;
+    case P3DFFTCU_K_DCT4:  // z_i = x_i w_i (i < n), -x_{2n-1-i} w_i (i >= n)
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        const C x = cmul(X(i < n ? i : M - 1 - i), __ldg(&tw2[i]));
+        v[m] = i < n ? x : cneg(x);
+      }
+      break;
+    default:  // P3DFFTCU_K_DST4: z_i = x_i w_i (i < n), +x_{2n-1-i} w_i (i >= n)
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = t + m * TP;
+        v[m] = cmul(X(i < n ? i : M - 1 - i), __ldg(&tw2[i]));
+      }
+      break;
+  }
+}
+
+// output index and value of core output F[idx] for the r2r kind (k outside [0, n): not an output)
+template <typename T>
+__device__ __forceinline__ int r2r_post(const StageParams &Q, int idx, typename cx<T>::type &y) {
+  typedef typename cx<T>::type C;
+  const C *__restrict__ tw2 = (const C *)Q.tw2;
+  const C *__restrict__ tw3 = (const C *)Q.tw3;
+  const int n = Q.n_out;
+  switch (Q.kind) {
+    case P3DFFTCU_K_DST1: y = cmuli(y); return idx - 1;
+    case P3DFFTCU_K_DCT2: if (idx < n) y = cmul(y, __ldg(&tw2[idx])); return idx;
+    case P3DFFTCU_K_DST2: if (idx >= 1 && idx <= n) y = cmuli(cmul(y, __ldg(&tw2[idx]))); return idx - 1;
+    case P3DFFTCU_K_DCT4: if (idx < n) y = cmul(y, __ldg(&tw3[idx])); return idx;
+    case P3DFFTCU_K_DST4: if (idx < n) y = cmuli(cmul(y, __ldg(&tw3[idx]))); return idx;
+    default: return idx;  // DCT1, DCT3, DST3
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 // SY = 1: tile groups with wait / signal flags (SyncDev, common.cuh) -- the persistent kernels of an overlapped pair
 template <typename T, int M, int KIND, int P, int TS, int SY>
@@ -294,7 +400,9 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
   constexpr bool r2c = KIND == P3DFFTCU_K_R2C, c2r = KIND == P3DFFTCU_K_C2R;
   constexpr bool bwd = KIND == P3DFFTCU_K_C2C_BWD || c2r;
   constexpr int twscale = (r2c || c2r) ? 2 : 1;  // the table is exp(-2 pi i j / nfft), nfft = 2M in the real cases
-  constexpr unsigned bytes = (unsigned)(Cfg::NIN * Cfg::csz);  // one pencil (R2C: 2M reals = M complex-sized elements)
+  constexpr bool r2r = KIND == kPipeR2R;
+  // one pencil (R2C: 2M reals = M complex-sized elements; r2r kinds: n real or complex values, rounded up to 16 bytes by the host)
+  const unsigned bytes = r2r ? (unsigned)Q.pipe_bytes : (unsigned)(Cfg::NIN * Cfg::csz);
   // R2C with a third pass of radix 2, 4 or 8 (M = 512, 1024, 2048: the 1024-, 2048- and 4096-point real transforms): the
   // last pass works on NS = M/R3 columns; the thread that owns the butterflies of column j = t + TP b (b < NB/2) also takes
   // those of the mirror column NS - j, so Z[k] = Z[j + NS q] and its Hermitian partner Z[M-k] = Z[(NS-j) + NS (R3-1-q)] both
@@ -394,7 +502,8 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
       mbar_expect_tx(bar, live ? bytes : 0u);
       if (live) {
         const long long base = u * Q.is_u + v * Q.is_v;
-        const void *src = r2c ? (const void *)((const T *)Q.in + base) : (const void *)((const C *)Q.in + base);
+        const bool real_in = r2c || (r2r && Q.dt_in == 1);  // strides count elements of the input's own type
+        const void *src = real_in ? (const void *)((const T *)Q.in + base) : (const void *)((const C *)Q.in + base);
         bulk_g2s(BA, src, bytes, bar);
       }
     }
@@ -472,6 +581,8 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
         C e = cmuli(cmul(d, w));
         v[m] = cconj(cadd(s, e));
       }
+    } else if constexpr (r2r) {
+      r2r_load<T, M, E>(v, BA, tA, Q);
     } else {
 #pragma unroll
       for (int m = 0; m < E; m++) {
@@ -631,6 +742,21 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
           }
         }
       }
+    } else if constexpr (r2r) {
+      if (live) {  // only the first n of the M core outputs are results (shifted by one for the sine kinds I / II)
+        const bool direct = Q.nseg == 1 && Q.deriv_g <= 0 && Q.dt_out == 2;
+        const SegDev &sg = Q.seg[0];
+        C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v;
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+          C y = v[m];
+          const int k = r2r_post<T>(Q, tB + m * TP, y);
+          if (k >= 0 && k < Q.n_out) {
+            if (direct) st_out(out + (long long)k * sg.os_d, y);
+            else store_out<T>(Q, k, uo, vo, y);
+          }
+        }
+      }
     } else if (live) {
       if (Q.nseg == 1 && Q.deriv_g <= 0) {  // local stage: one base pointer, constant stride between a thread's stores
         const SegDev &sg = Q.seg[0];
@@ -706,10 +832,16 @@ template <typename T, int M, int KIND, int P, int TS> const PipeInfo *pipe_info_
   if constexpr (!Cfg::valid) {
     return nullptr;
   } else {
-    static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, pipe_sync_launcher<T, M, KIND, P, TS>,
-                                  (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, (const void *)pow2_pipe_sync_kernel<T, M, KIND, P, TS>,
-                                  Cfg::THREADS, TS, Cfg::MINB, Cfg::smem};
-    return &info;
+    if constexpr (KIND == kPipeR2R) {  // (no tile-group form: an r2r stage of an overlapped pair runs chunk by chunk)
+      static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, nullptr, (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, nullptr,
+                                    Cfg::THREADS, TS, Cfg::MINB, Cfg::smem};
+      return &info;
+    } else {
+      static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, pipe_sync_launcher<T, M, KIND, P, TS>,
+                                    (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, (const void *)pow2_pipe_sync_kernel<T, M, KIND, P, TS>,
+                                    Cfg::THREADS, TS, Cfg::MINB, Cfg::smem};
+      return &info;
+    }
   }
 }
 

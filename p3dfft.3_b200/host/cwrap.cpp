@@ -303,5 +303,11 @@ int p3dfft_b200_stage_times(int plan, float *ms, int max_stages) {
   return (int)t.size();
 }
 int p3dfft_b200_have_device(void) { return b200::gpu_ready() ? 1 : 0; }
+void p3dfft_b200_set_host_staging(const char *mode) { b200::set_host_staging(mode); }
+void p3dfft_b200_host_release(const void *ptr) {
+  if (!b200::gpu_ready()) return;
+  p3dfftcu_stream_sync(b200::current_stream());
+  p3dfftcu_host_unpin(ptr);
+}
 
 }  // extern "C"

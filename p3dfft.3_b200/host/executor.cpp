@@ -178,8 +178,33 @@ void *workspace_bounce(long long bytes) {
   return g_bounce;
 }
 
+// device staging of host arrays (and of device arrays a bulk copy cannot read), shared by all plans: [0] input, [1] output
+static void *g_stage[2] = {nullptr, nullptr};
+static long long g_stage_bytes[2] = {0, 0};
+void *workspace_stage(int which, long long bytes) {
+  if (bytes < 16) bytes = 16;  // (a rank without local elements still gets a valid pointer)
+  if (g_stage_bytes[which] < bytes) {
+    p3dfftcu_stream_sync(current_stream());
+    if (g_stage[which]) p3dfftcu_free(g_stage[which]);
+    g_stage[which] = nullptr;
+    g_stage_bytes[which] = 0;
+    if (p3dfftcu_malloc(&g_stage[which], (size_t)bytes)) return nullptr;
+    g_stage_bytes[which] = bytes;
+  }
+  return g_stage[which];
+}
+
 void workspace_release() {
   Workspace &ws = g_ws;
+  for (int i = 0; i < 2; i++) {
+    if (g_stage[i]) p3dfftcu_free(g_stage[i]);
+    g_stage[i] = nullptr;
+    g_stage_bytes[i] = 0;
+  }
+  if (gpu_ready()) {
+    p3dfftcu_stream_sync(current_stream());
+    p3dfftcu_host_unpin_all();
+  }
   if (g_bounce) p3dfftcu_free(g_bounce);
   g_bounce = nullptr;
   g_bounce_bytes = 0;
@@ -210,6 +235,7 @@ static inline int peer_wr(const Plan *pl, const StagePlan &st, size_t q) { retur
 static void peer_barrier(Plan *pl, const StagePlan &st, void *stream) {
   Workspace &ws = g_ws;
   int n = (int)st.peers.size();
+  if (n > WS_MAX_RANKS) fatal(pl, "peer barrier among more than 64 ranks");
   void *pf[WS_MAX_RANKS];
   int slots[WS_MAX_RANKS];
   unsigned long long ep[WS_MAX_RANKS];
@@ -220,6 +246,48 @@ static void peer_barrier(Plan *pl, const StagePlan &st, void *stream) {
     ep[q] = ++ws.epoch_with[wr];
   }
   GPU(p3dfftcu_peer_barrier(pf, slots, n, ws.flags, ws.world_rank, ep, stream), pl, "peer barrier");
+}
+
+// ---- host arrays.  The reference's users pass ordinary heap arrays (sample/C++/test3D_r2c.C:197-205), i.e. pageable memory,
+// which a bare cudaMemcpy moves at a fraction of the PCIe rate.  Modes (P3DFFT_B200_HOST_STAGING or p3dfft_b200_set_host_staging):
+//   ring      (default) copy through a ring of pinned chunks, the CPU side split over a few threads and overlapped with the DMA;
+//             touches nothing of the user's address space
+//   register  page-lock the user's array on first use and remember the range (p3dfftcu_host_pin): full PCIe rate from the second
+//             call on, but the application must call p3dfft_b200_host_release() before it frees such an array (a stale
+//             registration of a re-used address range would make the DMA engine read the old pages)
+//   plain     a bare cudaMemcpyAsync
+// Arrays the application page-locked itself (cudaHostAlloc / cudaHostRegister) always take the direct asynchronous copy.
+enum { HOST_REGISTER = 0, HOST_RING = 1, HOST_PLAIN = 2 };
+static int g_host_mode = -1;
+static int parse_host_mode(const char *e) {
+  if (e && !strcmp(e, "register")) return HOST_REGISTER;
+  if (e && !strcmp(e, "plain")) return HOST_PLAIN;
+  return HOST_RING;
+}
+void set_host_staging(const char *mode) { g_host_mode = parse_host_mode(mode); }
+static int host_mode() {
+  if (g_host_mode < 0) g_host_mode = parse_host_mode(getenv("P3DFFT_B200_HOST_STAGING"));
+  return g_host_mode;
+}
+// true: copy with the ring (synchronous); false: [host, host+bytes) can be copied by an asynchronous cudaMemcpy
+static bool host_needs_ring(const void *host, size_t bytes) {
+  const int m = host_mode();
+  if (m == HOST_PLAIN || bytes < ((size_t)1 << 20)) return false;
+  if (p3dfftcu_host_is_pinned(host) == 1) return false;  // page-locked by the application, or registered earlier
+  if (m == HOST_REGISTER) return p3dfftcu_host_pin(host, bytes) != 0;
+  return true;
+}
+static void copy_in(const Plan *pl, void *dev, const void *host, size_t bytes, void *stream) {
+  if (host_needs_ring(host, bytes)) GPU(p3dfftcu_memcpy_staged(dev, host, bytes, 0, stream), pl, "host->device copy (staging ring)");
+  else GPU(p3dfftcu_memcpy(dev, host, bytes, 0, stream), pl, "host->device copy");
+}
+// returns when `host` holds the data
+static void copy_out(const Plan *pl, void *host, const void *dev, size_t bytes, void *stream) {
+  if (host_needs_ring(host, bytes)) GPU(p3dfftcu_memcpy_staged(host, dev, bytes, 1, stream), pl, "device->host copy (staging ring)");
+  else {
+    GPU(p3dfftcu_memcpy(host, dev, bytes, 1, stream), pl, "device->host copy");
+    GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");
+  }
 }
 
 // CTA budgets of an overlapped pair: the exchange stage is NVLink-bound (SM-issued peer stores top out at 717 GB/s per GPU
@@ -358,13 +426,10 @@ static void run_pair_sync(Plan *pl, size_t s, const void *ssrc, void *ldst, cons
   pair_caps(np, &xcap, &lcap);
   if (((uintptr_t)ssrc) % 16) {
     // bulk copies need 16-byte aligned pencils and every rank must follow the same protocol: an odd user pointer is staged
-    if (pl->dev_in_bytes < first.in_bytes) {
-      if (pl->dev_in) p3dfftcu_free(pl->dev_in);
-      GPU(p3dfftcu_malloc(&pl->dev_in, (size_t)first.in_bytes), pl, "staging allocation");
-      pl->dev_in_bytes = first.in_bytes;
-    }
-    GPU(p3dfftcu_memcpy(pl->dev_in, ssrc, (size_t)first.in_bytes, 2, stream), pl, "device copy");
-    ssrc = pl->dev_in;
+    void *st_in = workspace_stage(0, first.in_bytes);
+    if (!st_in) fatal(pl, "staging allocation");
+    GPU(p3dfftcu_memcpy(st_in, ssrc, (size_t)first.in_bytes, 2, stream), pl, "device copy");
+    ssrc = st_in;
   }
   // group tables: chunk c of a stage = the range [c0, c1) of chunk_dim, everything along its other pencil dimension
   p3dfftcu_sync sl, sx;
@@ -606,29 +671,22 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
   const bool out_dev = p3dfftcu_pointer_is_device(out) == 1;
   const void *src = in;
   void *dst = out;
-  if (!in_dev) {
-    if (pl->dev_in_bytes < pl->in_bytes) {
-      if (pl->dev_in) p3dfftcu_free(pl->dev_in);
-      GPU(p3dfftcu_malloc(&pl->dev_in, (size_t)pl->in_bytes), pl, "staging allocation");
-      pl->dev_in_bytes = pl->in_bytes;
-    }
-    GPU(p3dfftcu_memcpy(pl->dev_in, in, (size_t)pl->in_bytes, 0, stream), pl, "host->device copy");
-    src = pl->dev_in;
+  if (!in_dev) {  // host arrays are staged in device buffers shared by all plans of the process
+    void *st_in = workspace_stage(0, pl->in_bytes);
+    if (!st_in) fatal(pl, "staging allocation");
+    copy_in(pl, st_in, in, (size_t)pl->in_bytes, stream);
+    src = st_in;
   }
   if (!out_dev) {
-    if (pl->dev_out_bytes < pl->out_bytes) {
-      if (pl->dev_out) p3dfftcu_free(pl->dev_out);
-      GPU(p3dfftcu_malloc(&pl->dev_out, (size_t)pl->out_bytes), pl, "staging allocation");
-      pl->dev_out_bytes = pl->out_bytes;
-    }
-    dst = pl->dev_out;
+    dst = workspace_stage(1, pl->out_bytes);
+    if (!dst) fatal(pl, "staging allocation");
   }
   const size_t S = pl->stages.size();
   const bool timing = timers_on();
   std::vector<void *> &ev = pl->events;
   size_t ev0 = 0;  // first event of this exec: every exec since the last read keeps its own S+1 events (up to 64 execs)
   if (timing) {
-    if (pl->timed_execs >= 64) pl->timed_execs = 0;
+    if (pl->timed_execs >= 64) plan_collect_times(pl, false);  // the event ring is full: fold its 64 execs into the sums first
     ev0 = (size_t)pl->timed_execs * (S + 1);
     while (ev.size() < ev0 + S + 1) {
       void *e = nullptr;
@@ -702,8 +760,7 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
     if (timing) GPU(p3dfftcu_event_record(ev[ev0 + s + 1], stream), pl, "event");
   }
   if (!out_dev) {
-    GPU(p3dfftcu_memcpy(out, dst, (size_t)pl->out_bytes, 1, stream), pl, "device->host copy");
-    GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");
+    copy_out(pl, out, dst, (size_t)pl->out_bytes, stream);
   } else if (!in_dev) {
     GPU(p3dfftcu_stream_sync(stream), pl, "stream synchronise");  // the host input may be reused by the caller
   }
@@ -712,23 +769,32 @@ void plan_exec(Plan *pl, const void *in, void *out, int idir, bool OW) {
   pl->last_deriv_stage = deriv_stage;
 }
 
-// per-stage milliseconds averaged over the execs since the last read (waits for them to finish); also feeds p3dfft::timers
-void plan_collect_times(Plan *pl) {
-  if (!pl->events_valid || pl->timed_execs < 1) return;
+// per-stage milliseconds averaged over the execs since the last read (waits for them to finish); also feeds p3dfft::timers.
+// final = false: only folds the recorded execs into the running sums (the event ring holds 64 execs)
+void plan_collect_times(Plan *pl, bool final) {
   const size_t S = pl->stages.size();
-  for (size_t s = 0; s < S; s++) {
-    double sum = 0;
-    for (int x = 0; x < pl->timed_execs; x++) {
-      float ms = 0;
-      const size_t e = (size_t)x * (S + 1) + s;
-      GPU(p3dfftcu_event_elapsed(pl->events[e], pl->events[e + 1], &ms), pl, "event");
-      sum += ms;
+  if (pl->acc_ms.size() != S) pl->acc_ms.assign(S, 0.0);
+  if (pl->events_valid && pl->timed_execs >= 1) {
+    for (size_t s = 0; s < S; s++) {
+      double sum = 0;
+      for (int x = 0; x < pl->timed_execs; x++) {
+        float ms = 0;
+        const size_t e = (size_t)x * (S + 1) + s;
+        GPU(p3dfftcu_event_elapsed(pl->events[e], pl->events[e + 1], &ms), pl, "event");
+        sum += ms;
+      }
+      pl->acc_ms[s] += sum;
+      add_timer(pl->stages[s], (int)s == pl->last_deriv_stage, sum * 1e-3);
     }
-    pl->stage_ms[s] = (float)(sum / pl->timed_execs);
-    add_timer(pl->stages[s], (int)s == pl->last_deriv_stage, sum * 1e-3);
+    pl->acc_execs += pl->timed_execs;
   }
   pl->events_valid = false;
   pl->timed_execs = 0;
+  if (final && pl->acc_execs > 0) {
+    for (size_t s = 0; s < S; s++) pl->stage_ms[s] = (float)(pl->acc_ms[s] / pl->acc_execs);
+    pl->acc_ms.assign(S, 0.0);
+    pl->acc_execs = 0;
+  }
 }
 
 }  // namespace b200
@@ -754,26 +820,20 @@ template <class Type> void compute_deriv(Type *in, Type *out, DataGrid *gr, int 
   const size_t bytes = (size_t)sd[0] * sd[1] * sd[2] * 2 * prec;
   void *stream = b200::current_stream();
   const bool in_dev = p3dfftcu_pointer_is_device(in) == 1, out_dev = p3dfftcu_pointer_is_device(out) == 1;
-  void *din = (void *)in, *dout = (void *)out, *tmp_in = nullptr, *tmp_out = nullptr;
-  if (!in_dev) {
-    GPU(p3dfftcu_malloc(&tmp_in, bytes), nullptr, "staging allocation");
-    GPU(p3dfftcu_memcpy(tmp_in, in, bytes, 0, stream), nullptr, "host->device copy");
-    din = tmp_in;
-  }
-  if (!out_dev) {
-    if (tmp_in) dout = tmp_in;
-    else {
-      GPU(p3dfftcu_malloc(&tmp_out, bytes), nullptr, "staging allocation");
-      dout = tmp_out;
+  void *din = (void *)in, *dout = (void *)out;
+  if (!in_dev || !out_dev) {
+    // host arrays: one device scratch kept across calls (the kernel works in place on it)
+    void *scratch = b200::workspace_bounce((long long)bytes);
+    if (!scratch) b200::fatal(nullptr, "staging allocation");
+    if (!in_dev) {
+      b200::copy_in(nullptr, scratch, in, bytes, stream);
+      din = scratch;
     }
+    if (!out_dev) dout = scratch;
   }
   GPU(p3dfftcu_deriv(din, dout, prec, sd, ldir, g, gr->GlobStart[idir], stream), nullptr, "derivative kernel");
-  if (!out_dev) {
-    GPU(p3dfftcu_memcpy(out, dout, bytes, 1, stream), nullptr, "device->host copy");
-    GPU(p3dfftcu_stream_sync(stream), nullptr, "stream synchronise");
-  } else if (!in_dev) GPU(p3dfftcu_stream_sync(stream), nullptr, "stream synchronise");
-  if (tmp_in) p3dfftcu_free(tmp_in);
-  if (tmp_out) p3dfftcu_free(tmp_out);
+  if (!out_dev) b200::copy_out(nullptr, out, dout, bytes, stream);
+  else if (!in_dev) GPU(p3dfftcu_stream_sync(stream), nullptr, "stream synchronise");
 }
 
 template void compute_deriv<mycomplex>(mycomplex *, mycomplex *, DataGrid *, int);

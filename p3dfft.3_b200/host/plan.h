@@ -93,10 +93,9 @@ struct Plan {
   std::vector<void *> events;  // (S+1) CUDA events per exec recorded around the stages while timers are on
   int timed_execs;             // execs recorded since the stage times were last read (events [0, timed_execs*(S+1)))
   bool events_valid;
+  std::vector<double> acc_ms;  // sums of the execs already folded out of the event ring (it holds 64 execs)
+  int acc_execs;
   int last_deriv_stage;
-  // device staging for host-pointer calls
-  void *dev_in, *dev_out;
-  long long dev_in_bytes, dev_out_bytes;
   // overlapped pairs: high-priority side stream for the exchange stage, fork/join and per-chunk events
   void *xstream;
   std::vector<void *> sync_events;
@@ -106,7 +105,7 @@ struct Plan {
 };
 
 std::string describe(const Plan &p);
-void plan_collect_times(Plan *p);
+void plan_collect_times(Plan *p, bool final = true);
 
 // process-global device workspace shared by all plans: two ping-pong buffers and one flag array, mapped into the peers
 // with CUDA IPC.  Everything that names a peer is keyed by its rank in MPI_COMM_WORLD, so plans on different
@@ -145,8 +144,11 @@ Workspace &workspace();
 bool workspace_reserve(long long bytes, MPI_Comm comm, int nranks, int rank, std::string *err, std::vector<int> *world_of);
 // lazily grown local scratch of this rank alone (single-stage in == out calls)
 void *workspace_bounce(long long bytes);
+// device staging buffers for host arrays: which = 0 input, 1 output; grown on demand, shared by all plans
+void *workspace_stage(int which, long long bytes);
 void workspace_release();
 
+void set_host_staging(const char *mode);
 bool gpu_ready();
 void *current_stream();
 

@@ -591,7 +591,7 @@ bool finish_plan(Plan *pl, const std::vector<ProtoStage> &protos, const std::vec
 
 Plan::Plan()
     : ok(false), prec(0), dt_in(0), dt_out(0), nranks(1), rank(0), comm(MPI_COMM_NULL), g1(nullptr), g2(nullptr), pgrid(nullptr),
-      in_bytes(0), out_bytes(0), work_bytes(0), timed_execs(0), events_valid(false), last_deriv_stage(-1), dev_in(nullptr), dev_out(nullptr), dev_in_bytes(0), dev_out_bytes(0), xstream(nullptr), ctl(nullptr) {}
+      in_bytes(0), out_bytes(0), work_bytes(0), timed_execs(0), events_valid(false), acc_execs(0), last_deriv_stage(-1), xstream(nullptr), ctl(nullptr) {}
 
 Plan::~Plan() {
   for (size_t s = 0; s < stages.size(); s++) {
@@ -604,8 +604,6 @@ Plan::~Plan() {
   for (size_t i = 0; i < sync_events.size(); i++) p3dfftcu_event_destroy(sync_events[i]);
   if (xstream) p3dfftcu_stream_destroy(xstream);
   if (ctl) p3dfftcu_free(ctl);
-  if (dev_in) p3dfftcu_free(dev_in);
-  if (dev_out) p3dfftcu_free(dev_out);
   delete g1;
   delete g2;
   delete pgrid;

@@ -124,18 +124,45 @@ def test_fastcore_kinds_and_bluestein(emu, orc, name, n):
     """r2r kinds and non-power-of-two lengths on the register FFT core (fastcore_stage.cuh), transform dimension leading,
     strided, and with a transposing output order"""
     tol = TOL[4] if name.endswith("_S") else TOL[8]
-    assert run_1d(emu, orc, (n, 3, 2), name, 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
+    fc = ("fastcore", "pipe<")  # (r2r pencils a bulk copy can take go to the TMA-fed kernel: test_r2r_kinds_on_pipe_kernel)
+    assert run_1d(emu, orc, (n, 3, 2), name, 0, (0, 1, 2), (0, 1, 2), expect_variant=fc) < tol
     assert run_1d(emu, orc, (3, n, 2), name, 1, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
-    assert run_1d(emu, orc, (2, 5, n), name, 2, (0, 1, 2), (2, 0, 1), expect_variant="fastcore") < tol
+    assert run_1d(emu, orc, (2, 5, n), name, 2, (0, 1, 2), (2, 0, 1), expect_variant=fc) < tol
+
+
+@pytest.mark.parametrize("kind", [k for k in R2R_KINDS if k != "DCT4"])
+def test_r2r_kinds_on_pipe_kernel(emu, orc, kind, monkeypatch):
+    """every r2r kind whose symmetric extension has a power-of-two length L on the TMA-fed kernel (KIND = kPipeR2R): complex and
+    real data, double and single, contiguous and transposed stores, L = 64 (8 values per thread), 128 and 512 (three passes);
+    then the same transform with P3DFFT_B200_NO_PIPE_R2R=1 (fastcore, the fallback for unaligned pointers)"""
+    n_of = {"DCT1": lambda L: L // 2 + 1, "DST1": lambda L: L // 2 - 1}.get(kind, lambda L: L // 2)
+    for L in (64, 128, 512):
+        n = n_of(L)
+        for variant in ("COMPLEX_D", "REAL_D", "COMPLEX_S"):
+            name = f"{kind}_{variant}"
+            tol = TOL[4] if variant.endswith("_S") else TOL[8]
+            bytes_ = n * (16 if variant == "COMPLEX_D" else 8)
+            pipe = "pipe<" if bytes_ % 16 == 0 else "fastcore"  # dense user arrays: no room for a rounded-up bulk copy
+            assert run_1d(emu, orc, (n, 3, 2), name, 0, (0, 1, 2), (0, 1, 2), expect_variant=pipe) < tol, (name, L)
+            if L <= 128:
+                assert run_1d(emu, orc, (n, 9, 2), name, 0, (0, 1, 2), (1, 0, 2), expect_variant=pipe) < tol, (name, L, "transposed")
+    monkeypatch.setenv("P3DFFT_B200_NO_PIPE_R2R", "1")
+    assert run_1d(emu, orc, (n_of(128), 3, 2), f"{kind}_COMPLEX_D", 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < TOL[8]
 
 
 def test_fastcore_in_3d_with_derivative(emu, orc):
-    """config C4's shape in small: R2C(x), C2C(y), DCT-I(z) with z = 2^k+1 (core directly) and 2^k (Bluestein)"""
+    """config C4's shape in small: R2C(x), C2C(y), DCT-I(z) with z = 2^k+1 (core directly; the TMA-fed r2r kernel when the
+    padded intermediate rows leave room for the rounded-up bulk copy) and 2^k (Bluestein)"""
     t = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
     for nz in (33, 32):
         n = (16, 12, nz)
         assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
         assert run_3d(emu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=2) < TOL[8]
+    ts = ["R2CFFT_S", "CFFT_FORWARD_S", "DCT1_COMPLEX_S"]  # 65 x 8 bytes: the copy takes 8 bytes of the row padding
+    err, _, _, desc = run_3d(emu, orc, (16, 12, 65), half((16, 12, 65)), ts, (0, 1, 2), (1, 2, 0), cs2=0, return_all=True)
+    assert err < TOL[4] and any("r2r" in s["variant"] for s in desc["stages"]), [s["variant"] for s in desc["stages"]]
+    err, _, _, desc = run_3d(emu, orc, (16, 12, 65), half((16, 12, 65)), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=2, return_all=True)
+    assert err < TOL[8] and any("r2r" in s["variant"] for s in desc["stages"]), [s["variant"] for s in desc["stages"]]
     assert run_3d(emu, orc, (100, 12, 10), (100, 12, 10), CCC, (0, 1, 2), (2, 1, 0)) < TOL[8]
     n = (90, 40, 26)  # Bluestein R2C / C2R (Hermitian extension) round the 3D transform
     assert run_3d(emu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]

@@ -107,9 +107,82 @@ def test_fastcore_kinds_and_bluestein(gpu, orc, name, n):
     """r2r kinds and non-power-of-two lengths on the register FFT core (fastcore_stage.cuh): core sizes 64...4096,
     directly (L a power of two) and through Bluestein; leading, strided and transposing layouts"""
     tol = TOL[4] if name.endswith("_S") else TOL[8]
-    assert run_1d(gpu, orc, (n, 5, 3), name, 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
+    fc = ("fastcore", "pipe<")  # (r2r pencils a bulk copy can take go to the TMA-fed kernel: test_r2r_kinds_on_pipe_kernel)
+    assert run_1d(gpu, orc, (n, 5, 3), name, 0, (0, 1, 2), (0, 1, 2), expect_variant=fc) < tol
     assert run_1d(gpu, orc, (9, n, 2), name, 1, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < tol
-    assert run_1d(gpu, orc, (2, 17, n), name, 2, (0, 1, 2), (2, 0, 1), expect_variant="fastcore") < tol
+    assert run_1d(gpu, orc, (2, 17, n), name, 2, (0, 1, 2), (2, 0, 1), expect_variant=fc) < tol
+
+
+@pytest.mark.parametrize("kind", [k for k in R2R_KINDS if k != "DCT4"])
+@pytest.mark.parametrize("L", [64, 256, 1024, 4096])
+def test_r2r_kinds_on_pipe_kernel(gpu, orc, kind, L, monkeypatch):
+    """every r2r kind whose symmetric extension has a power-of-two length L on the TMA-fed kernel (pow2_pipe.cuh, KIND =
+    kPipeR2R): complex and real data, double and single, contiguous and transposed stores, partial tiles; then the fallback"""
+    n = {"DCT1": L // 2 + 1, "DST1": L // 2 - 1}.get(kind, L // 2)
+    for variant in ("COMPLEX_D", "REAL_D", "COMPLEX_S", "REAL_S"):
+        name = f"{kind}_{variant}"
+        tol = TOL[4] if variant.endswith("_S") else TOL[8]
+        esz = {"COMPLEX_D": 16, "REAL_D": 8, "COMPLEX_S": 8, "REAL_S": 4}[variant]
+        want = "pipe<" if (n * esz) % 16 == 0 else "fastcore"  # dense user arrays: no room for a rounded-up bulk copy
+        assert run_1d(gpu, orc, (n, 21, 3), name, 0, (0, 1, 2), (0, 1, 2), expect_variant=want) < tol, name
+        assert run_1d(gpu, orc, (n, 21, 3), name, 0, (0, 1, 2), (1, 0, 2), expect_variant=want) < tol, (name, "transposed")
+        assert run_1d(gpu, orc, (5, 6, n), name, 2, (1, 2, 0), (0, 1, 2), expect_variant=want) < tol, (name, "v-transposed")
+    monkeypatch.setenv("P3DFFT_B200_NO_PIPE_R2R", "1")
+    assert run_1d(gpu, orc, (n, 21, 3), f"{kind}_COMPLEX_D", 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < TOL[8]
+
+
+def test_config_c4_full_size_against_oracle(gpu, orc):
+    """BASELINE config 4 at its full size, 512 x 512 x 513 double: R2C(x) C2C(y) DCT-I(z) with the fused d/dx, against the
+    oracle (the DCT stage reads padded 513-element rows by bulk copy: the r2r form of the TMA-fed kernel), and backward"""
+    n = (512, 512, 513)
+    t = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
+    err, _, _, desc = run_3d(gpu, orc, n, half(n), t, (0, 1, 2), (1, 2, 0), cs2=0, deriv=0, return_all=True)
+    assert err < TOL[8]
+    assert any("r2r" in s["variant"] for s in desc["stages"]), [s["variant"] for s in desc["stages"]]
+    tb = ["C2RFFT_D", "CFFT_BACKWARD_D", "DCT1_COMPLEX_D"]
+    G = orc.transform_global(orc.random_field(n), t)  # a spectrum whose backward transform is real
+    err, _, _, desc = run_3d(gpu, orc, half(n), n, tb, (1, 2, 0), (0, 1, 2), cs1=0, G=G, return_all=True)
+    assert err < TOL[8]
+
+
+def test_config_c5_shape_2048_point_stages(gpu, orc):
+    """BASELINE config 5's stage shapes: 2048-point single-precision R2C(x) and C2C(y) stages on a 2048 x 2048 x 8 slab, and
+    the 2048-point C2C(z) stage on 16 x 8 x 2048, forward and backward against the oracle"""
+    for n in ((2048, 2048, 8), (16, 8, 2048)):
+        assert run_3d(gpu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[4]
+        assert run_3d(gpu, orc, half(n), n, CCR_S, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[4]
+
+
+@pytest.mark.parametrize("mode", ["ring", "register", "plain"])
+def test_host_staging_modes(gpu, orc, mode):
+    """pageable host arrays through every staging mode of the library (pinned ring with threaded CPU copies, page-locking
+    the user's array, bare cudaMemcpy): 256^3 double (134 MB real, 135 MB complex: several ring chunks), twice each"""
+    import ctypes
+    n = (256, 256, 256)
+    gpu.dll.p3dfft_b200_set_host_staging(mode.encode())
+    try:
+        for _ in range(2):
+            assert run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
+        assert run_3d(gpu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
+    finally:
+        gpu.dll.p3dfft_b200_set_host_staging(b"ring")
+        gpu.dll.p3dfft_b200_host_release(ctypes.c_void_p(0))
+
+
+def test_known_answer_at_bench_size_1024(gpu, orc):
+    """the reference sample's own known-answer test (sine field -> +-N/8 i at the modes (1, +-1, +-1), zero elsewhere;
+    sample/C++/test3D_r2c.C:281-331, 343-369) at the headline size 1024^3 double, device resident -- a consistent
+    wavenumber permutation passes the round-trip and Parseval properties but not this"""
+    torch = pytest.importorskip("torch")
+    import bench
+    prob = bench.Problem(gpu, "r2c", (1024, 1024, 1024), False, [1, 1, 1])
+    x = torch.empty(prob.n1e, device="cuda", dtype=torch.float64)
+    X = torch.empty(prob.n2e, device="cuda", dtype=torch.complex128)
+    err = bench.known_answer_check(torch, prob, x, X, torch.float64, torch.complex128, TOL[8])
+    assert err < 1e-14 * 1024 * 0.25, err  # the reference's own gate, relative to the peak N/8
+    del x, X
+    torch.cuda.empty_cache()
+    prob.free()
 
 
 def test_fastcore_3d_c4_literal_and_bluestein_real(gpu, orc):
