@@ -28,10 +28,17 @@ $(OBJDIR)/gpu_layer.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) in
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-# pipelined pow2 kernels: one object per (precision, kind); kind 5 = every r2r kind (DCT/DST I-IV)
-PIPEKEYS := 4_1 4_2 4_3 4_4 4_5 8_1 8_2 8_3 8_4 8_5
+# pipelined pow2 kernels: one object per (precision, kind); kind 5 = DCT-I on complex data, 13 = every r2r kind (DCT/DST I-IV) with the kind read at run time
+PIPEKEYS := 4_1 4_2 4_3 4_4 4_5 4_13 8_1 8_2 8_3 8_4 8_5 8_13
 PIPEOBJ  := $(PIPEKEYS:%=$(OBJDIR)/pipe_%.o)
 $(OBJDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+
+# smooth lengths 3|5|7 x 2^k: one object per (precision, kind)
+MIXKEYS := 4_1 4_2 4_3 4_4 8_1 8_2 8_3 8_4
+MIXOBJ  := $(MIXKEYS:%=$(OBJDIR)/mixed_%.o)
+$(OBJDIR)/mixed_%.o: $(PKG)/csrc/mixed_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
 
@@ -39,7 +46,7 @@ $(OBJDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(OBJDIR)/fastcore_inst.o $(PIPEOBJ)
+$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(OBJDIR)/fastcore_inst.o $(PIPEOBJ) $(MIXOBJ)
 	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static -ldl -lrt -lpthread
 
 emu: $(EMULIB)
@@ -53,10 +60,14 @@ EMUPIPEOBJ := $(PIPEKEYS:%=$(EMUDIR)/pipe_%.o)
 $(EMUDIR)/pipe_%.o: $(PKG)/csrc/pow2_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
 	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+EMUMIXOBJ := $(MIXKEYS:%=$(EMUDIR)/mixed_%.o)
+$(EMUDIR)/mixed_%.o: $(PKG)/csrc/mixed_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
+	@mkdir -p $(EMUDIR)
+	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
 $(EMUDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
 	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -c $< -o $@
-$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUDIR)/fastcore_inst.o $(EMUPIPEOBJ)
+$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUDIR)/fastcore_inst.o $(EMUPIPEOBJ) $(EMUMIXOBJ)
 	$(CXX) -shared -o $@ $^ -lrt -lpthread
 
 clean:

@@ -844,7 +844,13 @@ def main():
         # the device-resident arrays are not needed any more: give their memory to the library's staging buffers
         del x, X, Xbuf
         torch.cuda.empty_cache()
+        if not DRY:
+            free_b, total_b = torch.cuda.mem_get_info()
+            sys.stderr.write(f"[bench rank {rank}] before the host-array leg: {free_b / 1e9:.1f} GB of {total_b / 1e9:.1f} GB device memory free, "
+                             f"torch holds {torch.cuda.memory_reserved() / 1e9:.1f} GB; staging needs {hb / 1e9:.1f} GB\n")
         try:
+            if not DRY and hb > free_b:
+                raise RuntimeError(f"device staging buffers of {hb / 1e9:.1f} GB do not fit next to the work buffers ({free_b / 1e9:.1f} GB free)")
             hX = torch.empty(max(n2, 1), dtype=cdt).pin_memory()[:n2]
             dt = run_host(hx, hX, args.e2e_steps)
             e2e = {"value": 2 * flops_3d(n) / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": hb_all, "d2h_bytes_per_step": hb_all,
@@ -852,7 +858,7 @@ def main():
                    "numa": numa}
             del hX
         except RuntimeError as e:
-            e2e = {"value": None, "unit": "GFLOP/s", "why": f"pinned host allocation failed: {e}"[:200]}
+            e2e = {"value": None, "unit": "GFLOP/s", "why": f"host-array leg skipped: {e}"[:300]}
         if not args.no_pageable and e2e.get("value"):
             # what a user of the reference passes: plain heap arrays.  "ring" (the library's default): pinned staging ring with a
             # multi-threaded CPU copy; "register": the library page-locks the arrays on first use (the untimed first call pays)

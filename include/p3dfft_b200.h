@@ -43,7 +43,8 @@ int p3dfft_b200_stage_times(int plan, float *ms, int max_stages);
 /* 1 if a usable CUDA device was found at p3dfft_setup() (plans can be built and inspected without one) */
 int p3dfft_b200_have_device(void);
 /* How host arrays passed to exec calls cross PCIe (also the environment variable P3DFFT_B200_HOST_STAGING):
- *   "ring" (default)  through a ring of pinned chunks, CPU copy on P3DFFT_B200_HOST_THREADS (4) threads overlapped with the DMA
+ *   "ring" (default)  through a ring of pinned chunks, CPU copy on P3DFFT_B200_HOST_THREADS threads (default: cores / ranks, at
+ *                     most 8) overlapped with the DMA
  *   "register"        page-lock the array on first use (cudaHostRegister) and remember the range: full link rate from the second
  *                     call on; the application must call p3dfft_b200_host_release(ptr) before it frees such an array
  *   "plain"           a bare cudaMemcpyAsync
@@ -125,6 +126,8 @@ int p3dfftcu_host_unpin_all(void);
 /* host <-> device copy of a PAGEABLE array through a double-buffered ring of pinned chunks (the CPU copy of chunk c+1
  * overlaps the DMA of chunk c); kind 0 host->device, 1 device->host; returns when the copy is complete */
 int p3dfftcu_memcpy_staged(void *dst, const void *src, size_t bytes, int kind, void *stream);
+/* how many ranks of the job share this host: the ring's copy threads default to cores / ranks (at most 8) */
+void p3dfftcu_host_ranks_hint(int ranks_on_this_host);
 
 int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out);
 int p3dfftcu_stage_destroy(p3dfftcu_stage st);

@@ -21,23 +21,26 @@
 #include "generic_stage.cuh"
 #include "pow2_stage.cuh"
 #include "pow2_pipe.cuh"
+#include "mixed_pipe.cuh"
 #include "fastcore_stage.cuh"
 
 using namespace p3b;
 
 namespace p3b {
 #define P3B_DECL_PIPE(p, k) const PipeInfo *pipe_lookup_p##p##_##k(int ts, int M, int P);
-P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4) P3B_DECL_PIPE(4, 5)
-P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4) P3B_DECL_PIPE(8, 5)
+P3B_DECL_PIPE(4, 1) P3B_DECL_PIPE(4, 2) P3B_DECL_PIPE(4, 3) P3B_DECL_PIPE(4, 4) P3B_DECL_PIPE(4, 5) P3B_DECL_PIPE(4, 13)
+P3B_DECL_PIPE(8, 1) P3B_DECL_PIPE(8, 2) P3B_DECL_PIPE(8, 3) P3B_DECL_PIPE(8, 4) P3B_DECL_PIPE(8, 5) P3B_DECL_PIPE(8, 13)
 #undef P3B_DECL_PIPE
 const PipeInfo *pipe_lookup(int prec, int kind, int ts, int M, int P) {
-  if (kind >= P3DFFTCU_K_DCT1) kind = kPipeR2R;  // one kernel family for all r2r kinds
+  // r2r kinds: one kernel family with the kind read at run time (the caller asks for kPipeDCT1 to get the compile-time DCT-I)
+  if (kind >= P3DFFTCU_K_DCT1 && kind != kPipeDCT1) kind = kPipeR2R;
   if (prec == 4) switch (kind) {
       case 1: return pipe_lookup_p4_1(ts, M, P);
       case 2: return pipe_lookup_p4_2(ts, M, P);
       case 3: return pipe_lookup_p4_3(ts, M, P);
       case 4: return pipe_lookup_p4_4(ts, M, P);
       case 5: return pipe_lookup_p4_5(ts, M, P);
+      case 13: return pipe_lookup_p4_13(ts, M, P);
     }
   if (prec == 8) switch (kind) {
       case 1: return pipe_lookup_p8_1(ts, M, P);
@@ -45,6 +48,26 @@ const PipeInfo *pipe_lookup(int prec, int kind, int ts, int M, int P) {
       case 3: return pipe_lookup_p8_3(ts, M, P);
       case 4: return pipe_lookup_p8_4(ts, M, P);
       case 5: return pipe_lookup_p8_5(ts, M, P);
+      case 13: return pipe_lookup_p8_13(ts, M, P);
+    }
+  return nullptr;
+}
+#define P3B_DECL_MIX(p, k) const PipeInfo *mixed_lookup_p##p##_##k(int ts, int Q, int MC, int P);
+P3B_DECL_MIX(4, 1) P3B_DECL_MIX(4, 2) P3B_DECL_MIX(4, 3) P3B_DECL_MIX(4, 4)
+P3B_DECL_MIX(8, 1) P3B_DECL_MIX(8, 2) P3B_DECL_MIX(8, 3) P3B_DECL_MIX(8, 4)
+#undef P3B_DECL_MIX
+const PipeInfo *mixed_lookup(int prec, int kind, int ts, int Q, int MC, int P) {
+  if (prec == 4) switch (kind) {
+      case 1: return mixed_lookup_p4_1(ts, Q, MC, P);
+      case 2: return mixed_lookup_p4_2(ts, Q, MC, P);
+      case 3: return mixed_lookup_p4_3(ts, Q, MC, P);
+      case 4: return mixed_lookup_p4_4(ts, Q, MC, P);
+    }
+  if (prec == 8) switch (kind) {
+      case 1: return mixed_lookup_p8_1(ts, Q, MC, P);
+      case 2: return mixed_lookup_p8_2(ts, Q, MC, P);
+      case 3: return mixed_lookup_p8_3(ts, Q, MC, P);
+      case 4: return mixed_lookup_p8_4(ts, Q, MC, P);
     }
   return nullptr;
 }
@@ -461,13 +484,25 @@ int fast_setup(p3dfftcu_stage_s *st) {
 int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   const bool r2r = d.kind >= P3DFFTCU_K_DCT1;
   const bool real = d.kind == P3DFFTCU_K_R2C || d.kind == P3DFFTCU_K_C2R;
-  int M;
+  int M, mixQ = 0, mixMC = 0;
   if (r2r) {  // the kind's symmetric extension has a power-of-two length: DCT-I of 2^k+1 points, DST-I of 2^k-1, II-IV of 2^k
     M = internal_length(d.kind, d.nfft);
     if (M < 64 || M > 4096 || (M & (M - 1))) return -1;
-  } else {
-    if (!pow2_supported(d)) return -1;
+  } else if (pow2_supported(d)) {
     M = real ? d.nfft / 2 : d.nfft;
+  } else {
+    // smooth lengths: one odd factor 3, 5 or 7 times a power of two 128...1024 (mixed_pipe.cuh)
+    if (d.kind < P3DFFTCU_K_C2C_FWD || d.kind > P3DFFTCU_K_C2R) return -1;
+    if (real && (d.nfft % 2 || (d.kind == P3DFFTCU_K_C2R && d.nseg != 1))) return -1;
+    M = real ? d.nfft / 2 : d.nfft;
+    const char *nomix = getenv("P3DFFT_B200_NO_MIXED");
+    if (nomix && atoi(nomix)) return -1;
+    for (int q : {3, 5, 7})
+      if (M % q == 0) {
+        const int mc = M / q;
+        if (mc >= 128 && mc <= 1024 && (mc & (mc - 1)) == 0) { mixQ = q; mixMC = mc; }
+      }
+    if (!mixQ) return -1;
   }
   int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
   int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
@@ -489,9 +524,10 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   pp->bytes = (int)copy_bytes;
   const int ts = fout != 0;
   const size_t csz = (size_t)d.prec * (r2r ? d.dt_out : 2);  // element size of the output runs
-  const int E = pow2_values_per_thread(M), TP = M / E;
+  const int E = mixQ ? 16 : pow2_values_per_thread(M), TP = M / E;
   // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
-  int want = ts ? (int)(128 / csz) : (256 / TP > 0 ? 256 / TP : 1);
+  // (single precision: 8 pencils = 64-byte runs with twice the CTAs per SM measured 4-14 % faster than 16 pencils)
+  int want = ts ? (128 / csz > 8 ? 8 : (int)(128 / csz)) : (256 / TP > 0 ? 256 / TP : 1);
   if (d.whole_sm_ctas) {  // 512 threads at 128 registers (double) fill an SM
     const int w512 = 512 / TP > 0 ? 512 / TP : 1;
     if (w512 > want) want = w512;
@@ -504,15 +540,24 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   while (want > 1 && want / 2 >= ext) want /= 2;
   if (want > 16) want = 16;
   const PipeInfo *info = nullptr;
+  // DCT-I on complex data has a compile-time form; every other r2r kind (and DCT-I on real data) takes the run-time one
+  const int lkind = r2r ? ((d.kind == P3DFFTCU_K_DCT1 && d.dt_in == 2 && d.dt_out == 2) ? kPipeDCT1 : kPipeR2R) : d.kind;
+  auto lookup = [&](int p) { return mixQ ? mixed_lookup(d.prec, d.kind, ts, mixQ, mixMC, p) : pipe_lookup(d.prec, lkind, ts, M, p); };
+  if (mixQ && !ts) want = 384 / TP >= 2 ? 384 / TP : 2;  // (CTA-wide barriers: one CTA of up to 384 threads per SM)
+  if (mixQ) {  // round down to a power of two
+    int w2 = 1;
+    while (w2 * 2 <= want) w2 *= 2;
+    want = w2;
+  }
   int P = want;
   for (; P >= 1; P /= 2) {
-    info = pipe_lookup(d.prec, d.kind, ts, M, P);
+    info = lookup(P);
     if (info && info->smem <= g_smem_optin) break;
     info = nullptr;
   }
   if (!info) {  // small cores need several pencils to fill a warp
     for (P = want * 2; P <= 16 && !info; P *= 2) {
-      info = pipe_lookup(d.prec, d.kind, ts, M, P);
+      info = lookup(P);
       if (info && info->smem > g_smem_optin) info = nullptr;
       if (info) break;
     }
@@ -544,8 +589,11 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   long long g = (long long)g_num_sms * occ;
   pp->grid = (int)(pp->ntiles < g ? (pp->ntiles > 0 ? pp->ntiles : 1) : g);
   char nm[220];
-  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s%s> threads=%d tile=%dx%d%s store=%d smem=%zu grid=%d occ=%d",
-           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", r2r ? ",r2r" : "", info->threads, tu, tv,
+  char mix[32] = "";
+  if (mixQ) snprintf(mix, sizeof mix, ",%dx%d", mixQ, mixMC);
+  snprintf(nm, sizeof nm, "pipe<%s,M=%d,P=%d,%s%s%s> threads=%d tile=%dx%d%s store=%d smem=%zu grid=%d occ=%d",
+           d.prec == 8 ? "f64" : "f32", M, P, ts ? "transposed" : "contiguous", r2r ? (lkind == kPipeDCT1 ? ",r2r:dct1" : ",r2r") : "", mix,
+           info->threads, tu, tv,
            pp->vfast ? " v-fast" : "", pp->store_ord, info->smem, pp->grid, occ);
   *name = nm;
   return 0;
@@ -592,7 +640,15 @@ int p3dfftcu_init(int device) {
 }
 
 int p3dfftcu_malloc(void **ptr, size_t bytes) {
-  CK(cudaMalloc(ptr, bytes ? bytes : 16));
+  cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    size_t fr = 0, tot = 0;
+    cudaGetLastError();
+    cudaMemGetInfo(&fr, &tot);
+    char m[200];
+    snprintf(m, sizeof m, "cudaMalloc of %zu bytes: %s (device memory: %zu free of %zu)", bytes, cudaGetErrorString(e), fr, tot);
+    return failmsg(m);
+  }
   return 0;
 }
 int p3dfftcu_free(void *ptr) {
@@ -720,11 +776,14 @@ class CopyPool {
   bool stop_ = false;
 };
 CopyPool *g_pool = nullptr;
+int g_ranks_on_host = 1;
 CopyPool &copy_pool() {
   if (!g_pool) {
+    // default: the host's cores shared among the ranks of this job, at most 8 threads (one core copies ~10 GB/s)
     const char *e = getenv("P3DFFT_B200_HOST_THREADS");
-    int n = e ? atoi(e) : 4;
     const int hw = (int)std::thread::hardware_concurrency();
+    int n = e ? atoi(e) : (hw > 0 ? hw / (g_ranks_on_host > 0 ? g_ranks_on_host : 1) : 4);
+    if (!e && n > 8) n = 8;
     if (hw > 0 && n > hw) n = hw;
     if (n < 1) n = 1;
     g_pool = new CopyPool(n);
@@ -804,6 +863,8 @@ int p3dfftcu_host_unpin(const void *ptr) {
     if (a >= g_pins[i].base && a < g_pins[i].base + g_pins[i].bytes) pin_drop(i);
   return 0;
 }
+
+void p3dfftcu_host_ranks_hint(int ranks_on_this_host) { g_ranks_on_host = ranks_on_this_host > 0 ? ranks_on_this_host : 1; }
 
 int p3dfftcu_host_unpin_all(void) {
   while (!g_pins.empty()) pin_drop(g_pins.size() - 1);
@@ -943,7 +1004,9 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) 
     // r2r kinds whose symmetric extension has a power-of-two length, unit-stride aligned pencils: the TMA-fed kernel; the
     // variant chosen above stays as the fallback for input pointers a bulk copy cannot take
     const char *nopipe = getenv("P3DFFT_B200_NO_PIPE"), *nor2r = getenv("P3DFFT_B200_NO_PIPE_R2R");
-    if (!rc && allow_fast && d.kind >= P3DFFTCU_K_DCT1 && !(nopipe && atoi(nopipe)) && !(nor2r && atoi(nor2r))) {
+    const bool r2r_pipe = d.kind >= P3DFFTCU_K_DCT1 && !(nor2r && atoi(nor2r));
+    const bool mixed_pipe = d.kind >= P3DFFTCU_K_C2C_FWD && d.kind <= P3DFFTCU_K_C2R && !pow2_supported(d);  // 3|5|7 x 2^k
+    if (!rc && allow_fast && !(nopipe && atoi(nopipe)) && (r2r_pipe || mixed_pipe)) {
       std::string pname;
       int prc = pipe_setup(d, &st->pp, &pname);
       if (prc > 0) rc = failmsg("pipelined stage kernel setup failed");

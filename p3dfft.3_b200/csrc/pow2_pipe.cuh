@@ -166,8 +166,13 @@ constexpr size_t kPipeSmemMax = 232448 - 1024;  // 227 KB opt-in minus the stati
 
 // KIND of the kernel template: the P3DFFTCU_K_* value for C2C / R2C / C2R; kPipeR2R stands for EVERY r2r kind (DCT/DST I-IV,
 // real or complex data) whose internal FFT length L = M is a power of two -- which one is read from StageParams::kind at run
-// time (a CTA-uniform switch around the load and store loops; the M-point core in between is the same for all of them)
-constexpr int kPipeR2R = P3DFFTCU_K_DCT1;
+// time (a CTA-uniform switch around the load and store loops; the M-point core in between is the same for all of them).
+// kPipeDCT1 is the compile-time form of the one kind the BASELINE configurations use (DCT-I on complex data, the Chebyshev
+// direction of config 4): every index of the even extension and every live output is known at compile time, so the kernel
+// executes the C2C instruction stream (the runtime form needs three times as many instructions per pencil) and the unused
+// half of the last pass is dropped
+constexpr int kPipeR2R = 13;
+constexpr int kPipeDCT1 = P3DFFTCU_K_DCT1;
 
 template <typename T, int M, int KIND, int P, int TS> struct PipeCfg {
   enum { E = Pow2Cfg<M>::E, TP = M / E, THREADS = P * TP, XP0 = Pow2Smem<M>::PENCIL };
@@ -400,9 +405,9 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
   constexpr bool r2c = KIND == P3DFFTCU_K_R2C, c2r = KIND == P3DFFTCU_K_C2R;
   constexpr bool bwd = KIND == P3DFFTCU_K_C2C_BWD || c2r;
   constexpr int twscale = (r2c || c2r) ? 2 : 1;  // the table is exp(-2 pi i j / nfft), nfft = 2M in the real cases
-  constexpr bool r2r = KIND == kPipeR2R;
+  constexpr bool r2r = KIND == kPipeR2R, dct1 = KIND == kPipeDCT1;
   // one pencil (R2C: 2M reals = M complex-sized elements; r2r kinds: n real or complex values, rounded up to 16 bytes by the host)
-  const unsigned bytes = r2r ? (unsigned)Q.pipe_bytes : (unsigned)(Cfg::NIN * Cfg::csz);
+  const unsigned bytes = (r2r || dct1) ? (unsigned)Q.pipe_bytes : (unsigned)(Cfg::NIN * Cfg::csz);
   // R2C with a third pass of radix 2, 4 or 8 (M = 512, 1024, 2048: the 1024-, 2048- and 4096-point real transforms): the
   // last pass works on NS = M/R3 columns; the thread that owns the butterflies of column j = t + TP b (b < NB/2) also takes
   // those of the mirror column NS - j, so Z[k] = Z[j + NS q] and its Hermitian partner Z[M-k] = Z[(NS-j) + NS (R3-1-q)] both
@@ -583,6 +588,15 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
       }
     } else if constexpr (r2r) {
       r2r_load<T, M, E>(v, BA, tA, Q);
+    } else if constexpr (dct1) {
+      // even extension of the n = M/2 + 1 complex inputs: z_i = x_i (i <= M/2), x_{M-i} (i > M/2); i = tA + m TP, TP = M/E
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = tA + m * TP;
+        if (m < E / 2) v[m] = BA[i];
+        else if (m == E / 2) v[m] = BA[tA == 0 ? M / 2 : M - i];
+        else v[m] = BA[M - i];
+      }
     } else {
 #pragma unroll
       for (int m = 0; m < E; m++) {
@@ -742,6 +756,21 @@ __device__ __forceinline__ void pow2_pipe_body(const StageParams &Q, const SyncD
           }
         }
       }
+    } else if constexpr (dct1) {
+      if (live) {  // outputs k = tB + m TP <= M/2: m < E/2, and k = M/2 from the thread with tB = 0
+        if (Q.nseg == 1 && Q.deriv_g <= 0) {
+          const SegDev &sg = Q.seg[0];
+          C *out = (C *)sg.base + sg.off + uo * sg.os_u + vo * sg.os_v + (long long)tB * sg.os_d;
+          const long long step = (long long)TP * sg.os_d;
+#pragma unroll
+          for (int m = 0; m < E / 2; m++) st_out(out + m * step, v[m]);
+          if (tB == 0) st_out(out + (E / 2) * step, v[E / 2]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < E / 2; m++) store_out<T>(Q, tB + m * TP, uo, vo, v[m]);
+          if (tB == 0) store_out<T>(Q, M / 2, uo, vo, v[E / 2]);
+        }
+      }
     } else if constexpr (r2r) {
       if (live) {  // only the first n of the M core outputs are results (shifted by one for the sine kinds I / II)
         const bool direct = Q.nseg == 1 && Q.deriv_g <= 0 && Q.dt_out == 2;
@@ -832,7 +861,7 @@ template <typename T, int M, int KIND, int P, int TS> const PipeInfo *pipe_info_
   if constexpr (!Cfg::valid) {
     return nullptr;
   } else {
-    if constexpr (KIND == kPipeR2R) {  // (no tile-group form: an r2r stage of an overlapped pair runs chunk by chunk)
+    if constexpr (KIND == kPipeR2R || KIND == kPipeDCT1) {  // (no tile-group form: an r2r stage of an overlapped pair runs chunk by chunk)
       static const PipeInfo info = {pipe_launcher<T, M, KIND, P, TS>, nullptr, (const void *)pow2_pipe_kernel<T, M, KIND, P, TS>, nullptr,
                                     Cfg::THREADS, TS, Cfg::MINB, Cfg::smem};
       return &info;

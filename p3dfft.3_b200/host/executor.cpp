@@ -48,6 +48,7 @@ static bool ws_init(Workspace &ws, std::string *err) {
     ws.world_size = 0;
     return false;
   }
+  p3dfftcu_host_ranks_hint(ws.world_size);  // (one host: every rank of the world shares its cores)
   ws.peers.assign(ws.world_size, PeerMap());
   ws.epoch_with.assign(ws.world_size, 0);
   return true;

@@ -269,3 +269,30 @@ def test_reference_golden_vectors_single_rank(emu, orc):
     """every single-rank golden case (tests/golden: arrays written by the reference's own host code): all 36 memory-order
     pairs, C2R, the 1D API with the r2r kinds, stand-alone compute_deriv, the DCT4 registration quirk"""
     assert check_golden(emu, orc, None, rank=0, world=1) >= 100
+
+
+@pytest.mark.parametrize("q,mc", [(3, 128), (5, 128), (7, 128), (3, 256), (3, 512)])
+def test_smooth_lengths_on_mixed_radix_kernel(emu, orc, q, mc, monkeypatch):
+    """lengths M = q * 2^k (q = 3, 5, 7) on the TMA-fed mixed-radix kernel (mixed_pipe.cuh): C2C forward / backward, R2C / C2R of
+    2M points, contiguous and transposed stores, partial tiles, double and single; then Bluestein (P3DFFT_B200_NO_MIXED=1)"""
+    M = q * mc
+    e2 = ["EMPTY_TYPE_DOUBLE_COMPLEX"] * 2
+    small = mc <= 128
+    for types, n, n2, kw in ((["CFFT_FORWARD_D"] + e2, (M, 3, 2), (M, 3, 2), {}),
+                             (["CFFT_BACKWARD_D"] + e2, (M, 3, 2), (M, 3, 2), {}),
+                             (["R2CFFT_D"] + e2, (2 * M, 3, 2), (M + 1, 3, 2), dict(cs2=0)),
+                             (["C2RFFT_D"] + e2, (M + 1, 3, 2), (2 * M, 3, 2), dict(cs1=0))):
+        for mo2 in ((0, 1, 2), (1, 0, 2)) if small else ((0, 1, 2),):
+            err, _, _, desc = run_3d(emu, orc, n, n2, types, (0, 1, 2), mo2, return_all=True, **kw)
+            assert f",{q}x{mc}>" in desc["stages"][0]["variant"] or types[0].startswith("C2R"), desc["stages"][0]["variant"]
+            assert err < TOL[8], (types[0], mo2, err)
+    if small:
+        err, _, _, desc = run_3d(emu, orc, (M, 9, 2), (M, 9, 2), ["CFFT_FORWARD_S", "EMPTY_TYPE_SINGLE_COMPLEX", "EMPTY_TYPE_SINGLE_COMPLEX"],
+                                 (0, 1, 2), (1, 0, 2), return_all=True)
+        assert err < TOL[4] and f",{q}x{mc}>" in desc["stages"][0]["variant"], desc["stages"][0]["variant"]
+        n = (2 * M, 5, 3)
+        assert run_3d(emu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[4]
+        assert run_3d(emu, orc, half(n), n, CCR_S, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[4]
+        monkeypatch.setenv("P3DFFT_B200_NO_MIXED", "1")
+        err, _, _, desc = run_3d(emu, orc, (M, 3, 2), (M, 3, 2), ["CFFT_FORWARD_D"] + e2, (0, 1, 2), (0, 1, 2), return_all=True)
+        assert err < TOL[8] and "bluestein" in desc["stages"][0]["variant"], desc["stages"][0]["variant"]

@@ -131,6 +131,36 @@ def test_r2r_kinds_on_pipe_kernel(gpu, orc, kind, L, monkeypatch):
     assert run_1d(gpu, orc, (n, 21, 3), f"{kind}_COMPLEX_D", 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < TOL[8]
 
 
+@pytest.mark.parametrize("M", [384, 640, 768, 896, 1280, 1536, 1792, 2560, 3072, 3584, 5120])
+def test_smooth_lengths_on_mixed_radix_kernel(gpu, orc, M, monkeypatch):
+    """lengths M = q * 2^k (q = 3, 5, 7; 2^k = 128...1024) on the TMA-fed mixed-radix kernel (mixed_pipe.cuh) instead of
+    Bluestein: C2C forward / backward, R2C / C2R of 2M points, contiguous and transposed stores, partial tiles, both precisions"""
+    e2 = ["EMPTY_TYPE_DOUBLE_COMPLEX"] * 2
+    tag = [f",{q}x{M // q}>" for q in (3, 5, 7) if M % q == 0 and (M // q) & (M // q - 1) == 0]
+    for types, n, n2, kw in ((["CFFT_FORWARD_D"] + e2, (M, 21, 3), (M, 21, 3), {}),
+                             (["CFFT_BACKWARD_D"] + e2, (M, 21, 3), (M, 21, 3), {}),
+                             (["R2CFFT_D"] + e2, (2 * M, 21, 3), (M + 1, 21, 3), dict(cs2=0)),
+                             (["C2RFFT_D"] + e2, (M + 1, 21, 3), (2 * M, 21, 3), dict(cs1=0))):
+        for mo2 in ((0, 1, 2), (1, 0, 2), (2, 0, 1)):
+            err, _, _, desc = run_3d(gpu, orc, n, n2, types, (0, 1, 2), mo2, return_all=True, **kw)
+            assert any(t in desc["stages"][0]["variant"] for t in tag), desc["stages"][0]["variant"]
+            assert err < TOL[8], (types[0], mo2, err)
+    n = (2 * M, 10, 6)
+    assert run_3d(gpu, orc, n, half(n), RCC_S, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[4]
+    assert run_3d(gpu, orc, half(n), n, CCR_S, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[4]
+    assert run_3d(gpu, orc, (M, 10, 6), (M, 10, 6), CCC_S, (0, 1, 2), (1, 2, 0)) < TOL[4]
+
+
+def test_768_cubed_r2c_against_oracle(gpu, orc):
+    """768^3 double R2C forward (extra/makejob.py:131-134 sizes): 768-point real stage (3 x 128 core) and 768-point complex
+    stages (3 x 256) on the mixed-radix kernel, against the oracle"""
+    n = (768, 768, 192)
+    err, _, _, desc = run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0, return_all=True)
+    assert err < TOL[8]
+    assert all("pipe<" in s["variant"] for s in desc["stages"][:2]), [s["variant"] for s in desc["stages"]]
+    assert run_3d(gpu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
+
+
 def test_config_c4_full_size_against_oracle(gpu, orc):
     """BASELINE config 4 at its full size, 512 x 512 x 513 double: R2C(x) C2C(y) DCT-I(z) with the fused d/dx, against the
     oracle (the DCT stage reads padded 513-element rows by bulk copy: the r2r form of the TMA-fed kernel), and backward"""
@@ -156,17 +186,38 @@ def test_config_c5_shape_2048_point_stages(gpu, orc):
 @pytest.mark.parametrize("mode", ["ring", "register", "plain"])
 def test_host_staging_modes(gpu, orc, mode):
     """pageable host arrays through every staging mode of the library (pinned ring with threaded CPU copies, page-locking
-    the user's array, bare cudaMemcpy): 256^3 double (134 MB real, 135 MB complex: several ring chunks), twice each"""
+    the user's array, bare cudaMemcpy): 256^3 double (134 MB real, 135 MB complex: several ring chunks), the same arrays
+    twice (register mode: the second call finds the ranges page-locked), released before they are freed as
+    include/p3dfft_b200.h asks"""
     import ctypes
     n = (256, 256, 256)
+    pg = gpu.init_proc_grid([1, 1, 1])
+    g1 = gpu.init_data_grid(n, -1, pg, [0, 1, 2], [0, 1, 2])
+    g2 = gpu.init_data_grid(half(n), 0, pg, [1, 2, 0], [1, 2, 0])
+    pf = gpu.plan_3Dtrans(g1, g2, gpu.init_3Dtype(RCC))
+    pb = gpu.plan_3Dtrans(g2, g1, gpu.init_3Dtype(CCR))
+    G = orc.random_field(n)
+    og1 = orc.OGrid(n, [0, 1, 2], [0, 1, 2], [1, 1, 1], 0)
+    og2 = orc.OGrid(half(n), [1, 2, 0], [1, 2, 0], [1, 1, 1], 0, 0)
+    a = np.ascontiguousarray(orc.local_of(G, og1))
+    want = orc.local_of(orc.transform_global(G, RCC), og2)
+    out = np.empty(og2.storage_shape(), dtype=np.complex128)
+    back = np.empty_like(a)
     gpu.dll.p3dfft_b200_set_host_staging(mode.encode())
     try:
         for _ in range(2):
-            assert run_3d(gpu, orc, n, half(n), RCC, (0, 1, 2), (1, 2, 0), cs2=0) < TOL[8]
-        assert run_3d(gpu, orc, half(n), n, CCR, (1, 2, 0), (0, 1, 2), cs1=0) < TOL[8]
+            out[...] = np.nan
+            back[...] = np.nan
+            gpu.exec_3Dtrans(pf, a, out, 0)
+            gpu.exec_3Dtrans(pb, out, back, 0)
+            assert orc.rel_l2(out, want) < TOL[8]
+            assert orc.rel_l2(back / np.prod(n), a) < TOL[8]
     finally:
+        for arr in (a, out, back):
+            gpu.dll.p3dfft_b200_host_release(ctypes.c_void_p(arr.ctypes.data))
         gpu.dll.p3dfft_b200_set_host_staging(b"ring")
-        gpu.dll.p3dfft_b200_host_release(ctypes.c_void_p(0))
+        gpu.free_data_grid(g1)
+        gpu.free_data_grid(g2)
 
 
 def test_known_answer_at_bench_size_1024(gpu, orc):

@@ -91,6 +91,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 }
 // "device" allocations live in POSIX shared memory so that the CUDA-IPC calls below can map a peer
 // process's buffer: multi-rank exchanges (peer stores + flag barrier) run on the CPU exactly as written
+inline cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) { *fr = *tot = 0; return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n);
 cudaError_t cudaFree(void *p);
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }

@@ -15,6 +15,8 @@ import __graft_entry__ as ge  # noqa: E402
 
 
 def run(lib, name, gd1, gd2, types, mo1, mo2, single, cs2=-1, deriv=-1, reps=5):
+    if ONLY and ONLY not in name:
+        return
     pg = lib.init_proc_grid([1, 1, 1])
     g1 = lib.init_data_grid(gd1, -1, pg, [0, 1, 2], list(mo1))
     g2 = lib.init_data_grid(gd2, cs2, pg, [0, 1, 2], list(mo2))
@@ -57,6 +59,9 @@ def run(lib, name, gd1, gd2, types, mo1, mo2, single, cs2=-1, deriv=-1, reps=5):
     torch.cuda.empty_cache()
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""  # run only the shapes whose label contains this string
+
+
 def main():
     lib = ge.load_package().load().setup()
     lib.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -71,8 +76,10 @@ def main():
         ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"], (0, 1, 2), (1, 2, 0), False, cs2=0)
     run(lib, "1000x1000x200 C2C double (Bluestein on 2048 in x and y)", (1000, 1000, 200), (1000, 1000, 200), ["CFFT_FORWARD_D"] * 3,
         (0, 1, 2), (0, 1, 2), False)
-    run(lib, "768^3 R2C double (Bluestein)", (768, 768, 768), (385, 768, 768), ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], (0, 1, 2), (1, 2, 0),
+    run(lib, "768^3 R2C double (3 x 2^k mixed-radix kernel)", (768, 768, 768), (385, 768, 768), ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], (0, 1, 2), (1, 2, 0),
         False, cs2=0)
+    run(lib, "768^3 C2R double", (385, 768, 768), (768, 768, 768), ["C2RFFT_D", "CFFT_BACKWARD_D", "CFFT_BACKWARD_D"], (1, 2, 0), (0, 1, 2), False)
+    run(lib, "640^3 C2C double (5 x 128)", (640, 640, 640), (640, 640, 640), ["CFFT_FORWARD_D"] * 3, (0, 1, 2), (0, 1, 2), False)
     n = (1024, 1024, 1024)
     run(lib, "1024^3 R2C single mo 012->120", n, (513, 1024, 1024), ["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"], (0, 1, 2), (1, 2, 0), True, cs2=0)
     run(lib, "1024^3 C2R single mo 120->012", (513, 1024, 1024), n, ["C2RFFT_S", "CFFT_BACKWARD_S", "CFFT_BACKWARD_S"], (1, 2, 0), (0, 1, 2), True)
