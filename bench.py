@@ -701,6 +701,8 @@ def main():
         xc, yc = x[c0:c0 + (1 << 27)], y[c0:c0 + (1 << 27)]
         d2 += float((torch.linalg.vector_norm(yc / prob.norm - xc) ** 2).item())
         x2 += float((torch.linalg.vector_norm(xc) ** 2).item())
+    if n1:
+        del xc, yc  # (views: they would keep the arrays alive past the `del` before the host-array leg)
     rt_err = math.sqrt(reduce_ranks(d2, "sum") / reduce_ranks(x2, "sum"))
     parity["roundtrip_rel_l2"] = rt_err
     assert rt_err < tol, f"round-trip error {rt_err}"

@@ -44,7 +44,7 @@ int p3dfft_b200_stage_times(int plan, float *ms, int max_stages);
 int p3dfft_b200_have_device(void);
 /* How host arrays passed to exec calls cross PCIe (also the environment variable P3DFFT_B200_HOST_STAGING):
  *   "ring" (default)  through a ring of pinned chunks, CPU copy on P3DFFT_B200_HOST_THREADS threads (default: cores / ranks, at
- *                     most 8) overlapped with the DMA
+ *                     most 16) overlapped with the DMA
  *   "register"        page-lock the array on first use (cudaHostRegister) and remember the range: full link rate from the second
  *                     call on; the application must call p3dfft_b200_host_release(ptr) before it frees such an array
  *   "plain"           a bare cudaMemcpyAsync
@@ -126,7 +126,7 @@ int p3dfftcu_host_unpin_all(void);
 /* host <-> device copy of a PAGEABLE array through a double-buffered ring of pinned chunks (the CPU copy of chunk c+1
  * overlaps the DMA of chunk c); kind 0 host->device, 1 device->host; returns when the copy is complete */
 int p3dfftcu_memcpy_staged(void *dst, const void *src, size_t bytes, int kind, void *stream);
-/* how many ranks of the job share this host: the ring's copy threads default to cores / ranks (at most 8) */
+/* how many ranks of the job share this host: the ring's copy threads default to cores / ranks (at most 16) */
 void p3dfftcu_host_ranks_hint(int ranks_on_this_host);
 
 int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out);

@@ -779,11 +779,12 @@ CopyPool *g_pool = nullptr;
 int g_ranks_on_host = 1;
 CopyPool &copy_pool() {
   if (!g_pool) {
-    // default: the host's cores shared among the ranks of this job, at most 8 threads (one core copies ~10 GB/s)
+    // default: the host's cores shared among the ranks of this job, at most 16 threads (measured on a 16-core box, 1024^3
+    // double round trip, pinned 660 ms: 2 / 8 / 16 threads -> 2099 / 1034 / 830 ms; profiles/r02b_bench_c3_ring*.json)
     const char *e = getenv("P3DFFT_B200_HOST_THREADS");
     const int hw = (int)std::thread::hardware_concurrency();
     int n = e ? atoi(e) : (hw > 0 ? hw / (g_ranks_on_host > 0 ? g_ranks_on_host : 1) : 4);
-    if (!e && n > 8) n = 8;
+    if (!e && n > 16) n = 16;
     if (hw > 0 && n > hw) n = hw;
     if (n < 1) n = 1;
     g_pool = new CopyPool(n);

@@ -32,10 +32,12 @@ template <typename T, int MC, int Q, int KIND, int P, int TS> struct MixCfg {
   static constexpr size_t smem = bar_bytes + ((size_t)P * PITCH + T2N + T3N) * csz;
   static constexpr bool valid = (E == 16) && (THREADS % 32 == 0) && (THREADS >= 64) && (THREADS <= 768) && (P <= 16) &&
                                 (smem <= kPipeSmemMax) && (TS ? P >= 2 : true) && (sizeof(T) == 8 ? THREADS <= 512 : true);
+  // small CTAs (3 x 128 cores: 24 threads per pencil) share an SM in pairs: two independent CTAs overlap their phases
+  enum { MINB = THREADS <= 256 ? 2 : 1 };
 };
 
 template <typename T, int MC, int Q, int KIND, int P, int TS>
-__global__ void __launch_bounds__(MixCfg<T, MC, Q, KIND, P, TS>::THREADS, 1)
+__global__ void __launch_bounds__(MixCfg<T, MC, Q, KIND, P, TS>::THREADS, MixCfg<T, MC, Q, KIND, P, TS>::MINB)
 mixed_pipe_kernel(const __grid_constant__ StageParams S) {
   typedef typename cx<T>::type C;
   typedef MixCfg<T, MC, Q, KIND, P, TS> Cfg;
@@ -60,7 +62,8 @@ mixed_pipe_kernel(const __grid_constant__ StageParams S) {
   // same for contiguous output, lanes across the tile's pencils for transposed output
   const int slotA = tid / TP, tA = tid % TP;
   const int slotB = TS ? tid % P : slotA, tB = TS ? tid / P : tA;
-  const int qA = tA / TPC, tcA = tA % TPC, qB = tB / TPC, tcB = tB % TPC;
+  // store side: the group index runs fastest, so consecutive threads hold consecutive outputs k = qB + Q (tcB + TPC m)
+  const int qA = tA / TPC, tcA = tA % TPC, qB = tB % Q, tcB = tB / Q;
   const int puA = slotA & (tile_u - 1), pvA = slotA >> tu_log2;
   const int puB = slotB & (tile_u - 1), pvB = slotB >> tu_log2;
   C *BA = B + slotA * PITCH, *BB = B + slotB * PITCH;
@@ -102,20 +105,35 @@ mixed_pipe_kernel(const __grid_constant__ StageParams S) {
     mbar_wait(bar, parity);
     parity ^= 1;
 
+    if constexpr (c2r) {
+      // Hermitian pre-processing once per pencil, in place: Z[j] = (X[j] + conj X[M-j]) + i e^{+2 pi i j/N} (X[j] - conj X[M-j]),
+      // stored as conj Z for the conj-trick inverse.  Pairs (j, M-j), j = tA + TP m' < M/2; e^{+2 pi i (M-j)/N} = -conj(e^{...j})
+#pragma unroll
+      for (int mp = 0; mp < E / 2; mp++) {
+        const int j = tA + TP * mp;
+        C xa = BA[j], xb = BA[M - j];
+        if (j == 0) { xa.y = 0; xb.y = 0; }  // FFTW's c2r ignores Im X[0] and Im X[N/2]
+        const C w = cconj(__ldg(&tw[j]));   // e^{+2 pi i j/N}
+        {
+          const C b = cconj(xb), s = cadd(xa, b), d = csub(xa, b);
+          BA[j] = cconj(cadd(s, cmuli(cmul(d, w))));
+        }
+        if (j > 0) {
+          const C b = cconj(xa), s = cadd(xb, b), d = csub(xb, b);
+          BA[M - j] = cconj(cadd(s, cmuli(cmul(d, cneg(cconj(w))))));
+        }
+      }
+      if (tA == 0) {  // j = M/2 pairs with itself: e^{+2 pi i (M/2)/N} = i
+        const C x = BA[M / 2], b = cconj(x);
+        const C s = cadd(x, b), d = csub(x, b);
+        BA[M / 2] = cconj(cadd(s, cmuli(cmuli(d))));
+      }
+      __syncthreads();
+    }
     // ---------------- radix-Q step of group qA: v[m] = w_M^{n2 qA} sum_{n1} x[MC n1 + n2] w_Q^{n1 qA}, n2 = tcA + TPC m
     auto X = [&](int j) -> C {
-      if constexpr (c2r) {
-        // Z[j] = (X[j] + conj X[M-j]) + i e^{+2 pi i j/N} (X[j] - conj X[M-j]); conj Z for the conj-trick inverse
-        C a = BA[j];
-        C b = cconj(BA[M - j]);
-        if (j == 0) { a.y = 0; b.y = 0; }  // FFTW's c2r ignores Im X[0] and Im X[N/2]
-        const C s = cadd(a, b), d = csub(a, b);
-        const C e = cmuli(cmul(d, cconj(__ldg(&tw[j]))));
-        return cconj(cadd(s, e));
-      } else {
-        const C x = BA[j];
-        return bwd ? cconj(x) : x;
-      }
+      const C x = BA[j];
+      return (bwd && !c2r) ? cconj(x) : x;
     };
     C v[E];
 #pragma unroll
