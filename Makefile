@@ -7,9 +7,22 @@ PKG      := p3dfft.3_b200
 NVCC     := nvcc
 CXX      := g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-CXXFLAGS := -O2 -std=c++17 -fPIC -fno-gnu-unique -Wall -Wno-comment -Iinclude -Iinclude/compat -I$(PKG)/host
+# MPI=real : build against a real MPI (mpi.h / libmpi from MPI_INC / MPI_LIB, e.g. `mpicxx -show`) instead of the one-host
+#            mini-MPI of this repository (include/compat/mpi.h + host/minimpi.cpp, which would otherwise export MPI_* symbols
+#            with MPI_Comm = int and clash with the application's MPI).  Default: the mini-MPI (this image has no MPI).
+MPI      ?= mini
+ifeq ($(MPI),real)
+MPIINC   := $(MPI_INC)
+MPILIB   := $(MPI_LIB)
+MINIMPI  :=
+else
+MPIINC   := -Iinclude/compat
+MPILIB   :=
+MINIMPI  := minimpi
+endif
+CXXFLAGS := -O2 -std=c++17 -fPIC -fno-gnu-unique -Wall -Wno-comment -Iinclude $(MPIINC) -I$(PKG)/host
 NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fno-gnu-unique -Iinclude -I$(PKG)/csrc $(EXTRA_NVFLAGS)
-HOSTSRC  := geometry registry planner executor cwrap minimpi
+HOSTSRC  := geometry registry planner executor cwrap $(MINIMPI)
 LIBDIR   ?= $(PKG)/lib
 OBJDIR   := $(LIBDIR)/obj
 HOSTOBJ  := $(HOSTSRC:%=$(OBJDIR)/%.o)
@@ -47,7 +60,7 @@ $(OBJDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(OBJDIR)/fastcore_inst.o $(PIPEOBJ) $(MIXOBJ)
-	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static -ldl -lrt -lpthread
+	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static $(MPILIB) -ldl -lrt -lpthread
 
 emu: $(EMULIB)
 $(EMUDIR)/gpu_layer_emu.o: $(PKG)/csrc/gpu_layer.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h

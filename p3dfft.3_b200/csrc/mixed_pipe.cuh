@@ -62,8 +62,10 @@ mixed_pipe_kernel(const __grid_constant__ StageParams S) {
   // same for contiguous output, lanes across the tile's pencils for transposed output
   const int slotA = tid / TP, tA = tid % TP;
   const int slotB = TS ? tid % P : slotA, tB = TS ? tid / P : tA;
-  // store side: the group index runs fastest, so consecutive threads hold consecutive outputs k = qB + Q (tcB + TPC m)
-  const int qA = tA / TPC, tcA = tA % TPC, qB = tB % Q, tcB = tB / Q;
+  // (store side with the group index fastest -- consecutive threads holding consecutive outputs k = qB + Q (tcB + TPC m) --
+  //  was measured slower on both store forms: the gather from the Q sub-buffers then conflicts on the banks, 768-point C2C
+  //  1.58 vs 1.38 ms transposed, 1.68 vs 1.62 ms contiguous; profiles/r02b_/r02c_ncu_full_768.summary.csv)
+  const int qA = tA / TPC, tcA = tA % TPC, qB = tB / TPC, tcB = tB % TPC;
   const int puA = slotA & (tile_u - 1), pvA = slotA >> tu_log2;
   const int puB = slotB & (tile_u - 1), pvB = slotB >> tu_log2;
   C *BA = B + slotA * PITCH, *BB = B + slotB * PITCH;

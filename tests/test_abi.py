@@ -90,3 +90,47 @@ print("PLANS" + json.dumps(out))
     assert bwd["stages"][1]["segs"][0]["os_d"] == 520
     # user-visible arrays stay dense
     assert fwd["stages"][0]["in_stride"] == [1, 1024, 1024 * 1024] and bwd["stages"][0]["in_stride"] == [1024, 513 * 1024, 1]
+
+
+def _bench_dry_run(args, nranks=1, timeout=900):
+    """bench.py's own logic (configs, synthetic field, parity block, roofline bookkeeping, host-array legs) on the CPU-thread
+    emulation build with tiny grids: P3DFFT_BENCH_DRYRUN=1 prints {"dry_run": true, "would_print": {...}} instead of a metric line"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, P3DFFT_BENCH_DRYRUN="1")
+    env.pop("P3DFFT_B200_PLAN_ONLY", None)
+    if nranks > 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29700 + os.getpid() % 200), os.path.join(ROOT, "bench.py"), "--gpus", str(nranks)] + args
+    else:
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py")] + args
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout, cwd=ROOT)
+    lines = [x for x in out.stdout.splitlines() if x.startswith("{")]
+    assert out.returncode == 0 and lines, (out.stdout[-2000:], out.stderr[-3000:])
+    d = json.loads(lines[-1])
+    assert d["dry_run"] and d["emulated_library"]
+    return d["would_print"]
+
+
+@pytest.mark.parametrize("cfg,edge", [("c3", 32), ("c2", 16), ("c4", 16)])
+def test_bench_logic_dry_run(emu, cfg, edge):
+    d = _bench_dry_run(["--config", cfg, "--edge", str(edge), "--steps", "1", "--warmup", "1", "--e2e-steps", "1"])
+    tol = 1e-5 if cfg == "c2" else 1e-12
+    assert d["config"]["config"] == cfg and d["parity"]["roundtrip_rel_l2"] < tol
+    assert d["parity"]["oracle"]["fwd_rel_l2"] < tol and d["parity"]["oracle"]["bwd_rel_l2"] < tol
+    assert d["parity"]["known_answer"]["max_abs_err_over_peak"] < 10 * tol
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and "pageable" in d["e2e"] and "pageable_registered" in d["e2e"]
+    assert d["roofline"]["bound"] == "hbm" and len(d["roofline"]["stages"]) == 6 and d["gpu_launches"] > 0
+    if cfg == "c4":
+        assert d["parity"]["oracle"]["fwd_deriv_rel_l2"] < tol
+
+
+def test_bench_logic_dry_run_world_size_2(emu):
+    """the N > 1 path of bench.py under torch.distributed.run with gloo (world_size 2): per-rank blocks of the global Philox
+    field, per-rank known-answer and oracle checks reduced over the ranks, NVLink roofline bookkeeping of the exchange stages"""
+    d = _bench_dry_run(["--config", "c3", "--edge", "32", "--steps", "1", "--warmup", "1", "--e2e-steps", "1"], nranks=2)
+    assert d["n_gpus"] == 2 and d["config"]["proc_grid"] == [1, 1, 2]
+    assert d["parity"]["roundtrip_rel_l2"] < 1e-12 and d["parity"]["oracle"]["fwd_rel_l2"] < 1e-12
+    assert d["parity"]["known_answer"]["max_abs_err_over_peak"] < 1e-11
+    assert d["roofline"]["bound"] == "nvlink" and sum(1 for s in d["roofline"]["stages"] if s["exchange"]) == 2
