@@ -526,8 +526,10 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   const size_t csz = (size_t)d.prec * (r2r ? d.dt_out : 2);  // element size of the output runs
   const int E = mixQ ? 16 : pow2_values_per_thread(M), TP = M / E;
   // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
-  // (single precision: 8 pencils = 64-byte runs with twice the CTAs per SM measured 4-14 % faster than 16 pencils)
-  int want = ts ? (128 / csz > 8 ? 8 : (int)(128 / csz)) : (256 / TP > 0 ? 256 / TP : 1);
+  // (single precision, local stages: 8 pencils = 64-byte runs with twice the CTAs per SM measured 4-14 % faster than 16
+  //  pencils; exchange stages keep 128-byte runs where the tile fits: peer stores of 64-byte runs reach 580 instead of
+  //  717 GB/s, tools/microbench/peer_store_bench.cu)
+  int want = ts ? ((128 / csz > 8 && d.nseg == 1) ? 8 : (int)(128 / csz)) : (256 / TP > 0 ? 256 / TP : 1);
   if (d.whole_sm_ctas) {  // 512 threads at 128 registers (double) fill an SM
     const int w512 = 512 / TP > 0 ? 512 / TP : 1;
     if (w512 > want) want = w512;
