@@ -110,6 +110,40 @@ def cases():
     return cs
 
 
+STRIDE = 61  # kernel-size cases keep every 61st element of each rank's output (+ its L2 norm) instead of the whole array
+
+
+def large_cases():
+    """cases at the sizes the production kernels serve (M >= 64: TMA-fed power-of-two, r2r and mixed-radix kernels, exchange
+    segments) -- the small cases above pin the index mapping, these pin the kernels themselves to the reference's output"""
+    cs = []
+    n = (128, 64, 64)
+    cs += [fwd("k_fwd_128x64x64", n, [1, 1, 1]), bwd("k_bwd_128x64x64", n, [1, 1, 1]),
+           fwd("k_fwd_128x64x64_2x2", n, [1, 2, 2]), bwd("k_bwd_128x64x64_2x2", n, [1, 2, 2]),
+           fwd("k_fwd_128x64x64_slab4", n, [1, 1, 4]), fwd("k_fwd_deriv1_128x64x64_slab2", n, [1, 1, 2], idir=1),
+           fwd("k_fwd_single_128x64x64", n, [1, 1, 1], types=["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"])]
+    cs.append(fwd("k_fwd_2048x4x3", (2048, 4, 3), [1, 1, 1]))   # 1024-point complex core with the symmetric last pass
+    cs.append(bwd("k_bwd_2048x4x3", (2048, 4, 3), [1, 1, 1]))
+    cs.append(fwd("k_fwd_768x6x4", (768, 6, 4), [1, 1, 1]))     # mixed radix: 768-point real = 3 x 128 core
+    t4 = ["R2CFFT_D", "CFFT_FORWARD_D", "DCT1_COMPLEX_D"]
+    cs.append(fwd("k_c4_dct_64x16x129", (64, 16, 129), [1, 1, 1], types=t4))  # DCT-I of 2^k + 1 points on padded rows
+    cs.append(fwd("k_c4_dct_deriv0_64x16x129", (64, 16, 129), [1, 1, 1], types=t4, idir=0))
+    for ty, g, dim in (("CFFT_FORWARD_D", (1024, 4, 3), 0), ("CFFT_BACKWARD_D", (4096, 2, 2), 0), ("CFFT_FORWARD_S", (512, 4, 3), 0),
+                       ("CFFT_FORWARD_D", (768, 4, 3), 0), ("CFFT_BACKWARD_D", (640, 4, 3), 0), ("CFFT_FORWARD_D", (896, 3, 2), 0),
+                       ("R2CFFT_D", (1536, 4, 3), 0), ("DCT1_COMPLEX_D", (513, 4, 3), 0), ("DST1_COMPLEX_D", (255, 4, 3), 0),
+                       ("DCT2_REAL_D", (512, 4, 3), 0), ("DCT3_COMPLEX_D", (256, 4, 3), 0), ("DST2_REAL_D", (256, 4, 3), 0),
+                       ("DST3_REAL_D", (128, 4, 3), 0), ("DST4_REAL_D", (128, 4, 3), 0), ("CFFT_FORWARD_D", (4, 3, 1024), 2)):
+        kind = orc.type_info(ty)[0]
+        lead = {0: [0, 1, 2], 2: [1, 2, 0]}[dim]
+        other = {0: [1, 2, 0], 2: [0, 1, 2]}[dim]
+        for mo1, mo2 in ((lead, lead), (lead, other)):
+            g2 = half(g, dim) if kind == "r2c" else list(g)
+            tag = f"{ty}_{g[dim]}_d{dim}_" + "".join(map(str, mo1)) + "_" + "".join(map(str, mo2))
+            cs.append(dict(name=f"k_t1d_{tag}", mode="1d", types=[ty], dim=dim, procdims=[1, 1, 1], gdims1=list(g), gdims2=g2, cs1=-1,
+                           cs2=dim if kind == "r2c" else -1, idir=-1, dmap1=[0, 1, 2], mo1=mo1, dmap2=[0, 1, 2], mo2=mo2))
+    return cs
+
+
 def case_types(c):
     """(dt_in, dt_out, prec) and the numpy dtypes of a case"""
     if c["mode"] == "deriv":
@@ -218,6 +252,31 @@ def main():
         with open(os.path.join(HERE, "index.json"), "w") as f:
             json.dump(index, f, indent=0)
         print(f"{len(index)} cases -> tests/golden/reference_golden.npz")
+    # kernel-size cases: every STRIDE-th element of each rank's output and the output's L2 norm
+    bundle, index = {}, []
+    for c in large_cases():
+        if only and not any(o in c["name"] for o in only):
+            continue
+        with tempfile.TemporaryDirectory() as td:
+            try:
+                data, worst = run_case(c, td)
+            except Exception as e:
+                print(f"{c['name']:44s} REFERENCE FAILED: {str(e)[:300]}")
+                continue
+        tol = 1e-5 if case_types(c)[2] == 4 else 1e-12
+        print(f"{c['name']:44s} oracle vs reference rel-L2 {worst:.2e} {'ok' if worst < tol else 'MISMATCH'}")
+        for k, v in data.items():
+            if k.startswith("out_"):
+                bundle[f"{c['name']}/sub_{k[4:]}"] = v[::STRIDE].copy()
+                bundle[f"{c['name']}/norm_{k[4:]}"] = np.array([np.linalg.norm(v.astype(np.complex128 if np.iscomplexobj(v) else np.float64)), v.size])
+            else:
+                bundle[f"{c['name']}/{k}"] = v
+        index.append(c["name"])
+    if not only:
+        np.savez_compressed(os.path.join(HERE, "reference_golden_kernels.npz"), **bundle)
+        with open(os.path.join(HERE, "index_kernels.json"), "w") as f:
+            json.dump(index, f, indent=0)
+        print(f"{len(index)} kernel-size cases -> tests/golden/reference_golden_kernels.npz (every {STRIDE}th element + norms)")
 
 
 if __name__ == "__main__":

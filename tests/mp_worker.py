@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 import __graft_entry__ as ge  # noqa: E402
-from util import TOL, check_golden, np_dtype  # noqa: E402
+from util import TOL, check_golden, check_golden_kernels, np_dtype  # noqa: E402
 
 
 def main():
@@ -33,6 +33,7 @@ def main():
     worst = 0.0
     if sys.argv[2] == "golden":  # every golden case recorded on this many ranks, against the reference's own arrays
         n = check_golden(lib, orc, None, rank=rank, world=world)
+        n += check_golden_kernels(lib, orc, None, rank=rank, world=world)  # 128 x 64 x 64 on 2 and 4 ranks (exchange segments)
         assert n > 0, "no golden case for this world size"
     for c in cases:
         types, pd = c["types"], c["procdims"]

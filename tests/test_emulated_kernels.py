@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, FASTCORE_CASES, PERMS, R2R_KINDS, RCC, RCC_S, half
-from util import TOL, check_golden, run_1d, run_3d
+from util import TOL, check_golden, check_golden_kernels, run_1d, run_3d
 
 
 def fast_variant(name):
@@ -296,3 +296,11 @@ def test_smooth_lengths_on_mixed_radix_kernel(emu, orc, q, mc, monkeypatch):
         monkeypatch.setenv("P3DFFT_B200_NO_MIXED", "1")
         err, _, _, desc = run_3d(emu, orc, (M, 3, 2), (M, 3, 2), ["CFFT_FORWARD_D"] + e2, (0, 1, 2), (0, 1, 2), return_all=True)
         assert err < TOL[8] and "bluestein" in desc["stages"][0]["variant"], desc["stages"][0]["variant"]
+
+
+def test_reference_golden_vectors_at_kernel_sizes_emulated(emu, orc):
+    """a subset of the kernel-size golden cases on the emulation (the whole set runs on the GPU): 128 x 64 x 64 forward,
+    mixed-radix 768, DCT-I of 513 points, run-time r2r kinds"""
+    names = ["k_fwd_128x64x64", "k_fwd_768x6x4", "k_t1d_CFFT_FORWARD_D_768_d0_012_120", "k_t1d_DCT1_COMPLEX_D_513_d0_012_012",
+             "k_t1d_DCT2_REAL_D_512_d0_012_120", "k_t1d_DST1_COMPLEX_D_255_d0_012_012", "k_c4_dct_deriv0_64x16x129"]
+    assert check_golden_kernels(emu, orc, names, rank=0, world=1) == len(names)

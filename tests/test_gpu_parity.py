@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from cases import FASTCORE_CASES, CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
-from util import TOL, check_golden, run_1d, run_3d
+from util import TOL, check_golden, check_golden_kernels, run_1d, run_3d
 
 pytestmark = pytest.mark.gpu
 
@@ -326,3 +326,9 @@ def test_reference_golden_vectors_single_rank(gpu, orc):
     """every single-rank golden case (tests/golden: arrays written by the reference's own host code): all 36 memory-order
     pairs, C2R, the 1D API with the r2r kinds, stand-alone compute_deriv, the DCT4 registration quirk"""
     assert check_golden(gpu, orc, None, rank=0, world=1) >= 100
+
+
+def test_reference_golden_vectors_at_kernel_sizes(gpu, orc):
+    """the single-rank kernel-size golden cases (tests/golden/reference_golden_kernels.npz: outputs of the reference's own host
+    code at M >= 64): the TMA-fed power-of-two, r2r and mixed-radix kernels pinned to the reference, not only to the oracle"""
+    assert check_golden_kernels(gpu, orc, None, rank=0, world=1) >= 38

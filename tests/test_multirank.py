@@ -65,9 +65,10 @@ def test_pencil_2x2_config_c1_shape():
     launch(4, [fwd(n, [1, 2, 2]), bwd(n, [1, 2, 2]), fwd((16, 12, 10), [1, 2, 2]), bwd((16, 12, 10), [1, 2, 2])])
 
 
-@pytest.mark.parametrize("nranks", [3, 4])
+@pytest.mark.parametrize("nranks", [2, 3, 4])
 def test_reference_golden_vectors_multirank(nranks):
-    """per-rank outputs of the reference's own host code (tests/golden) on 3 and 4 ranks"""
+    """per-rank outputs of the reference's own host code (tests/golden) on 2, 3 and 4 ranks, including the kernel-size cases
+    (128 x 64 x 64 on slab and pencil grids: the TMA-fed kernels storing through the per-peer segment tables)"""
     launch(nranks, "golden")
 
 
@@ -216,8 +217,8 @@ def test_gpu_multirank_parity(nranks):
     cs.append(fwd((58, 139, 199), grids[0]))
     cs.append(bwd((58, 139, 199), grids[-1]))
     launch(nranks, cs, mode="gpu", timeout=1200)
-    if nranks == 4:
-        launch(4, "golden", mode="gpu")
+    if nranks in (2, 4):
+        launch(nranks, "golden", mode="gpu")
 
 
 @pytest.mark.gpu

@@ -55,6 +55,24 @@ def test_oracle_matches_reference_golden_vectors(gold, orc):
     assert worst[8] < 1e-14
 
 
+def test_oracle_matches_reference_golden_vectors_at_kernel_sizes(orc):
+    """the 42 kernel-size cases (128 x 64 x 64 on 1 / 2 / 4 ranks, 512...4096-point stages, 768 / 640 / 896 / 1536-point
+    mixed-radix lengths, r2r kinds with 128...1024-point extensions): sampled elements + norms of the reference's outputs"""
+    from util import compare_with_kernel_golden, golden_kernels
+    index, z, mg = golden_kernels()
+    assert len(index) == 42 and [c["name"] for c in mg.large_cases()] == index, "index_kernels.json is stale: rerun make_golden.py"
+    for name in index:
+        c = golden_case(z, name)
+        pd = c["procdims"]
+        G = mg.global_input(c)
+        prec = mg.case_types(c)[2]
+        for r in range(pd[0] * pd[1] * pd[2]):
+            og1, og2, want = mg.oracle_output(c, G, r)
+            assert og1.Ldims + og1.GlobStart + og2.Ldims + og2.GlobStart == list(z[f"{name}/meta_{r}"]), (name, r)
+            err = compare_with_kernel_golden(orc, z, mg, name, r, want.astype(mg.np_dtype(mg.case_types(c)[1], prec)), prec)
+            assert err < (1e-6 if prec == 4 else 1e-13), (name, r, err)
+
+
 def test_sample_known_answer_sine_spectrum(orc):
     """sample/C++/test3D_r2c.C:281-331: forward/N^3 of sin*sin*sin is +-0.125i at wavenumbers (1|N-1)^3"""
     n = (16, 12, 10)

@@ -166,3 +166,51 @@ def check_golden(lib, orc, names, rank=0, world=1):
             assert err < TOL[prec], (name, rank, err)
         done += 1
     return done
+
+
+# ------------------------------------------------------------------------------------------------ kernel-size golden vectors
+def golden_kernels():
+    """(index, npz, make_golden module) of tests/golden/reference_golden_kernels.npz: cases at the sizes the production kernels
+    serve (M >= 64), produced by the reference's host code; every STRIDE-th element of each rank's output + its L2 norm"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    with open(os.path.join(here, "index_kernels.json")) as f:
+        index = json.load(f)
+    return index, np.load(os.path.join(here, "reference_golden_kernels.npz")), mg
+
+
+def compare_with_kernel_golden(orc, z, mg, name, rank, out, prec):
+    """out: this rank's full output array; compares the sampled elements and the norm with the reference's"""
+    sub = z[f"{name}/sub_{rank}"]
+    norm, size = z[f"{name}/norm_{rank}"]
+    flat = np.asarray(out).ravel()
+    assert flat.size == int(size), (name, rank, flat.size, size)
+    if flat.size == 0:
+        return 0.0
+    err = orc.rel_l2(flat[::mg.STRIDE], sub)
+    mine = np.linalg.norm(flat.astype(np.complex128 if np.iscomplexobj(flat) else np.float64))
+    assert abs(mine - norm) <= (1e-5 if prec == 4 else 1e-12) * max(norm, 1e-300), (name, rank, mine, norm)
+    return err
+
+
+def check_golden_kernels(lib, orc, names=None, rank=0, world=1, expect_variants=None):
+    """run the kernel-size golden cases whose rank count equals `world` through the C ABI and compare with the reference"""
+    index, z, mg = golden_kernels()
+    done = 0
+    for name in names or index:
+        c = golden_case(z, name)
+        pd = c["procdims"]
+        if pd[0] * pd[1] * pd[2] != world:
+            continue
+        out, geo = exec_case(lib, orc, mg, c, rank)
+        assert geo == list(z[f"{name}/meta_{rank}"]), (name, geo)
+        prec = mg.case_types(c)[2]
+        err = compare_with_kernel_golden(orc, z, mg, name, rank, out, prec)
+        assert err < TOL[prec], (name, rank, err)
+        done += 1
+    return done
