@@ -25,9 +25,11 @@ PY
   tail -2 gpurun_out/${TAG}_bench_${name}_${N}gpu.err | cut -c1-300
 }
 run c3_slab P3DFFT_B200_OVERLAP_TRACE=0 -- 
+if [ "${QUICK:-0}" != "1" ]; then
 run c3_slab_notriple P3DFFT_B200_TRIPLE=0 -- --no-e2e --no-cpu --no-parity
 run c3_slab_trace P3DFFT_B200_OVERLAP_TRACE=1 -- --no-e2e --no-cpu --no-parity --steps 3
 if [ $N -ge 4 ]; then run c3_pencil P3DFFT_B200_OVERLAP_TRACE=0 -- --grid pencil --no-e2e --no-cpu; fi
+fi
 if [ $N -eq 4 ]; then run c4_2x2 P3DFFT_B200_OVERLAP_TRACE=0 -- --config c4 --no-cpu; run c1_2x2 P3DFFT_B200_OVERLAP_TRACE=0 -- --config c1 --no-cpu; fi
 if [ $N -eq 8 ]; then run c5_slab P3DFFT_B200_OVERLAP_TRACE=0 -- --config c5 --no-cpu --e2e-steps 3; fi
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
