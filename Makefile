@@ -55,11 +55,18 @@ $(OBJDIR)/mixed_%.o: $(PKG)/csrc/mixed_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
 
+# tensor-load kernels (strided inputs): one object per (precision, kind 1..3)
+TLKEYS := 4_1 4_2 4_3 8_1 8_2 8_3
+TLOBJ  := $(TLKEYS:%=$(OBJDIR)/tload_%.o)
+$(OBJDIR)/tload_%.o: $(PKG)/csrc/pow2_tload_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+
 $(OBJDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*.cuh) include/p3dfft_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(OBJDIR)/fastcore_inst.o $(PIPEOBJ) $(MIXOBJ)
+$(LIB): $(HOSTOBJ) $(OBJDIR)/gpu_layer.o $(OBJDIR)/fastcore_inst.o $(PIPEOBJ) $(MIXOBJ) $(TLOBJ)
 	$(CXX) -shared -o $@ $^ -L$(CUDA_HOME)/lib64 -lcudart_static $(MPILIB) -ldl -lrt -lpthread
 
 emu: $(EMULIB)
@@ -77,10 +84,14 @@ EMUMIXOBJ := $(MIXKEYS:%=$(EMUDIR)/mixed_%.o)
 $(EMUDIR)/mixed_%.o: $(PKG)/csrc/mixed_pipe_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
 	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
+EMUTLOBJ := $(TLKEYS:%=$(EMUDIR)/tload_%.o)
+$(EMUDIR)/tload_%.o: $(PKG)/csrc/pow2_tload_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
+	@mkdir -p $(EMUDIR)
+	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -DPIPE_PREC=$(word 1,$(subst _, ,$*)) -DPIPE_KIND=$(word 2,$(subst _, ,$*)) -c $< -o $@
 $(EMUDIR)/fastcore_inst.o: $(PKG)/csrc/fastcore_inst.cu $(wildcard $(PKG)/csrc/*.cuh) tools/cuda_emu/cuda_runtime.h
 	@mkdir -p $(EMUDIR)
 	$(CXX) -O1 -std=c++17 -fPIC -fno-gnu-unique -x c++ -Itools/cuda_emu -Iinclude -I$(PKG)/csrc -c $< -o $@
-$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUDIR)/fastcore_inst.o $(EMUPIPEOBJ) $(EMUMIXOBJ)
+$(EMULIB): $(HOSTOBJ) $(EMUDIR)/gpu_layer_emu.o $(EMUDIR)/emu_globals.o $(EMUDIR)/fastcore_inst.o $(EMUPIPEOBJ) $(EMUMIXOBJ) $(EMUTLOBJ)
 	$(CXX) -shared -o $@ $^ -lrt -lpthread
 
 clean:

@@ -66,6 +66,7 @@ struct StageParams {
   const void *chirp;    // Bluestein: c_j = exp(-i pi j^2 / L), j < L
   const void *bhat;     // Bluestein: FFT_M of the wrapped conj chirp, divided by M
   int pipe_bytes;   // TMA kernel, r2r kinds: bytes of one pencil's bulk copy (n_in elements rounded up to 16 bytes)
+  int tl_swap;      // tensor-load kernel: != 0 when the transform dimension is dim 2 of the tensor map (dims 1, 2 are ordered by stride)
   int deriv_g;      // > 0: spectral derivative epilogue with full length g
   int nseg;
   SegDev seg[P3DFFTCU_MAXSEG];

@@ -2,6 +2,9 @@
 // memory, twiddle tables, stage planning (kernel variant + tile shape) and launch, stand-alone
 // spectral derivative, CUDA-IPC peer mapping and the stream-ordered peer barrier.
 #include <cuda_runtime.h>
+#ifndef P3B_EMU
+#include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is reached through cudaGetDriverEntryPoint
+#endif
 #include <time.h>
 
 #include <atomic>
@@ -22,6 +25,7 @@
 #include "pow2_stage.cuh"
 #include "pow2_pipe.cuh"
 #include "mixed_pipe.cuh"
+#include "pow2_tload.cuh"
 #include "fastcore_stage.cuh"
 
 using namespace p3b;
@@ -49,6 +53,22 @@ const PipeInfo *pipe_lookup(int prec, int kind, int ts, int M, int P) {
       case 4: return pipe_lookup_p8_4(ts, M, P);
       case 5: return pipe_lookup_p8_5(ts, M, P);
       case 13: return pipe_lookup_p8_13(ts, M, P);
+    }
+  return nullptr;
+}
+#define P3B_DECL_TL(p, k) const TLoadInfo *tload_lookup_p##p##_##k(int ts, int M, int P);
+P3B_DECL_TL(4, 1) P3B_DECL_TL(4, 2) P3B_DECL_TL(4, 3) P3B_DECL_TL(8, 1) P3B_DECL_TL(8, 2) P3B_DECL_TL(8, 3)
+#undef P3B_DECL_TL
+const TLoadInfo *tload_lookup(int prec, int kind, int ts, int M, int P) {
+  if (prec == 4) switch (kind) {
+      case 1: return tload_lookup_p4_1(ts, M, P);
+      case 2: return tload_lookup_p4_2(ts, M, P);
+      case 3: return tload_lookup_p4_3(ts, M, P);
+    }
+  if (prec == 8) switch (kind) {
+      case 1: return tload_lookup_p8_1(ts, M, P);
+      case 2: return tload_lookup_p8_2(ts, M, P);
+      case 3: return tload_lookup_p8_3(ts, M, P);
     }
   return nullptr;
 }
@@ -282,7 +302,7 @@ unsigned long long g_peer_timeout_ns = [] {
 }();
 
 // ------------------------------------------------------------------ stage object
-enum Variant { V_GENERIC = 0, V_POW2 = 1, V_PIPE = 2, V_FAST = 3 };
+enum Variant { V_GENERIC = 0, V_POW2 = 1, V_PIPE = 2, V_FAST = 3, V_TLOAD = 4 };
 
 struct PipePlan {
   const p3b::PipeInfo *info = nullptr;
@@ -291,6 +311,18 @@ struct PipePlan {
   long long tiles_u = 0, tiles_v = 0, ntiles = 0;
   int vfast = 0;
   int bytes = 0;  // r2r kinds: bytes of one pencil's bulk copy
+};
+
+// tensor-load kernel (pow2_tload.cuh): tile geometry + the TMA tensor map of the input, encoded for the last `in` pointer
+struct TLoadPlan {
+  const p3b::TLoadInfo *info = nullptr;
+  int M = 0, P = 0, grid = 0, along_u = 0, store_ord = 0, swap = 0;
+  long long tiles_u = 0, tiles_v = 0, ntiles = 0;
+  // geometry of the map: scalars of `prec` bytes; dim0 = the input's unit-stride dimension, dim1 = transform dimension, dim2 = the other
+  unsigned long long dim[3] = {0, 0, 0}, stride_b[2] = {0, 0};
+  unsigned box0 = 0, box1 = 0;
+  const void *encoded_for = nullptr;
+  p3b::TMapArg map;
 };
 
 struct FastPlan {
@@ -312,6 +344,7 @@ struct p3dfftcu_stage_s {
   Pow2Plan pw;
   PipePlan pp;
   FastPlan fp;
+  TLoadPlan tl;
   bool have_pw = false;  // the non-pipelined pow2 kernel is kept as the fallback for unaligned user pointers
   bool empty = false;    // no local pencils on this rank: exec is a no-op
   std::string name;
@@ -598,6 +631,115 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
            info->threads, tu, tv,
            pp->vfast ? " v-fast" : "", pp->store_ord, info->smem, pp->grid, occ);
   *name = nm;
+  return 0;
+}
+
+// picks the tensor-load kernel (pow2_tload.cuh) for a power-of-two stage whose input is unit-stride along u or v instead of
+// the transform dimension; returns 0 ok, <0 not applicable, >0 CUDA error
+int tload_setup(const p3dfftcu_stage_desc &d, TLoadPlan *tl, std::string *name) {
+  if (!pow2_supported(d) || d.kind == P3DFFTCU_K_C2R) return -1;
+  const char *off = getenv("P3DFFT_B200_NO_TLOAD");
+  if (off && atoi(off)) return -1;
+  const bool r2c = d.kind == P3DFFTCU_K_R2C;
+  const int M = r2c ? d.nfft / 2 : d.nfft;
+  const int fin = fastest(d.is_d, d.is_u, d.is_v, d.n_in, d.nu, d.nv);
+  const int fout = fastest(d.seg[0].os_d, d.seg[0].os_u, d.seg[0].os_v, d.seg[0].k1 - d.seg[0].k0, d.nu, d.nv);
+  if (fin == 0) return -1;
+  const bool along_u = fin == 1;
+  if ((along_u ? d.is_u : d.is_v) != 1) return -1;
+  const long long esz = (long long)d.prec * d.dt_in;
+  const long long s_other = along_u ? d.is_v : d.is_u, n_unit = along_u ? d.nu : d.nv, n_other = along_u ? d.nv : d.nu;
+  if ((d.is_d * esz) % 16 || (n_other > 1 && (s_other * esz) % 16)) return -1;
+  const int ts = fout != 0;
+  if (ts && fout != fin) return -1;  // transposed stores run across the SAME pencils: the output's unit-stride dimension must be the input's
+  int want = (int)(128 / esz);        // 128-byte box rows
+  if (want > 16) want = 16;
+  while (want > 4 && want / 2 >= n_unit) want /= 2;
+  const TLoadInfo *info = nullptr;
+  int P = want;
+  for (; P >= 4; P /= 2) {
+    info = tload_lookup(d.prec, d.kind, ts, M, P);
+    if (info && info->smem <= g_smem_optin && (P * esz) % 16 == 0) break;
+    info = nullptr;
+  }
+  if (!info) return -1;
+  tl->info = info;
+  tl->M = M;
+  tl->P = P;
+  tl->along_u = along_u ? 1 : 0;
+  tl->store_ord = fout == 0 ? ORD_D : (fout == 1 ? ORD_U : ORD_V);
+  tl->tiles_u = along_u ? (d.nu + P - 1) / P : d.nu;
+  tl->tiles_v = along_u ? d.nv : (d.nv + P - 1) / P;
+  tl->ntiles = tl->tiles_u * tl->tiles_v;
+  // tensor map geometry in scalars of `prec` bytes: dim0 = the unit-stride dimension; dims 1 and 2 ordered by stride
+  const unsigned long long sc = r2c ? 1 : 2;
+  const unsigned long long sd = (unsigned long long)(d.is_d * esz), so = (unsigned long long)((n_other > 1 ? s_other : d.is_d * d.n_in) * esz);
+  tl->dim[0] = (unsigned long long)n_unit * sc;
+  tl->box0 = (unsigned)(P * sc);
+  tl->box1 = (unsigned)info->boxrows;
+  const bool swap = so < sd;  // the other dimension has the smaller stride: it becomes dim 1
+  tl->swap = swap ? 1 : 0;
+  tl->dim[1] = swap ? (unsigned long long)n_other : (unsigned long long)d.n_in;
+  tl->dim[2] = swap ? (unsigned long long)d.n_in : (unsigned long long)n_other;
+  tl->stride_b[0] = swap ? so : sd;
+  tl->stride_b[1] = swap ? sd : so;
+  tl->encoded_for = nullptr;
+  if (cudaFuncSetAttribute(info->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info->smem) != cudaSuccess) return 1;
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, info->func, info->threads, info->smem) != cudaSuccess) return 1;
+  if (occ < 1) occ = 1;
+  const long long g = (long long)g_num_sms * occ;
+  tl->grid = (int)(tl->ntiles < g ? (tl->ntiles > 0 ? tl->ntiles : 1) : g);
+  char nm[220];
+  snprintf(nm, sizeof nm, "tload<%s,M=%d,P=%d,%s> threads=%d tile=%s%d rows=%d box=%ux%u%s smem=%zu grid=%d occ=%d", d.prec == 8 ? "f64" : "f32",
+           M, P, ts ? "transposed" : "contiguous", info->threads, along_u ? "u" : "v", P, info->rows, tl->box0, tl->box1, swap ? " d=dim2" : "",
+           info->smem, tl->grid, occ);
+  *name = nm;
+  return 0;
+}
+
+// encodes the TMA tensor map of the stage's input for `in` (cached: exec loops call with the same pointer)
+int tload_encode(TLoadPlan *tl, const p3dfftcu_stage_desc &d, const void *in) {
+  if (tl->encoded_for == in) return 0;
+  const bool swap = tl->swap != 0;
+#ifdef P3B_EMU
+  TMapArg &m = tl->map;
+  memset(&m, 0, sizeof m);
+  m.base = (const unsigned char *)in;
+  m.elem_bytes = (unsigned)d.prec;
+  m.dim0 = (unsigned)tl->dim[0]; m.dim1 = (unsigned)tl->dim[1]; m.dim2 = (unsigned)tl->dim[2];
+  m.stride1 = (long long)tl->stride_b[0]; m.stride2 = (long long)tl->stride_b[1];
+  m.box0 = tl->box0;
+  m.box1 = swap ? 1u : tl->box1;
+  m.box2 = swap ? tl->box1 : 1u;
+#else
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) {
+      cudaGetLastError();
+      fn = nullptr;
+    }
+    return (EncodeFn)fn;
+  }();
+  if (!encode) return failmsg("cuTensorMapEncodeTiled is not available");
+  static_assert(sizeof(CUtensorMap) == sizeof(TMapArg), "tensor map size");
+  cuuint64_t gdim[3] = {tl->dim[0], tl->dim[1], tl->dim[2]};
+  cuuint64_t gstr[2] = {tl->stride_b[0], tl->stride_b[1]};
+  cuuint32_t box[3] = {tl->box0, swap ? 1u : tl->box1, swap ? tl->box1 : 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(reinterpret_cast<CUtensorMap *>(&tl->map), d.prec == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                      const_cast<void *>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char m[160];
+    snprintf(m, sizeof m, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return failmsg(m);
+  }
+#endif
+  tl->encoded_for = in;
   return 0;
 }
 
@@ -992,6 +1134,14 @@ int p3dfftcu_stage_create(const p3dfftcu_stage_desc *desc, p3dfftcu_stage *out) 
         else if (prc == 0) {
           st->variant = V_PIPE;
           st->name = pname;
+        } else {
+          // unit stride along u or v instead of the transform dimension: TMA tensor loads of [row][P] tiles
+          int trc = tload_setup(d, &st->tl, &pname);
+          if (trc > 0) rc = failmsg("tensor-load stage kernel setup failed");
+          else if (trc == 0) {
+            st->variant = V_TLOAD;
+            st->name = pname;
+          }
         }
       }
     }
@@ -1058,7 +1208,24 @@ int p3dfftcu_stage_exec_capped(p3dfftcu_stage st, const void *in, void *const *d
     // bulk copies need 16-byte aligned sources; an odd user pointer takes the non-pipelined kernel instead
     if (((uintptr_t)in) % 16) variant = st->have_pw ? V_POW2 : st->fallback;
   }
-  if (variant == V_PIPE) {
+  if (variant == V_TLOAD) {
+    // tensor maps need a 16-byte aligned base; a failed encode (driver too old, geometry refused) retires the variant
+    if (((uintptr_t)in) % 16 || !st->tl.info || tload_encode(&st->tl, st->d, in)) {
+      if (st->tl.info && !(((uintptr_t)in) % 16)) st->tl.info = nullptr;
+      variant = V_POW2;
+    }
+  }
+  if (variant == V_TLOAD) {
+    const TLoadPlan &tl = st->tl;
+    if (tl.ntiles > 0) {
+      P.tile_u = tl.along_u ? tl.P : 1; P.tile_v = tl.along_u ? 1 : tl.P; P.tu_log2 = ilog2(P.tile_u);
+      P.load_ord = tl.along_u ? ORD_U : ORD_V; P.store_ord = tl.store_ord;
+      P.tiles_u = tl.tiles_u; P.tiles_v = tl.tiles_v; P.ntiles = tl.ntiles; P.tl_swap = tl.swap;
+      int grid = tl.grid;
+      if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+      tl.info->launch(P, tl.map, grid, cs);
+    }
+  } else if (variant == V_PIPE) {
     const PipePlan &pp = st->pp;
     if (pp.ntiles > 0) {
       P.tile_u = pp.tile_u; P.tile_v = pp.tile_v; P.tu_log2 = pp.tu_log2;

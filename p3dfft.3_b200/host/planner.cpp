@@ -92,11 +92,18 @@ int lead_dim(const int mo[3], const int ld[3]) {
   return best < 0 ? 0 : best;
 }
 
+// P3DFFT_B200_COST_ROWROW / P3DFFT_B200_COST_TLOAD: A/B overrides of two weights of the layout search (development)
+double env_cost(const char *name, double dflt) {
+  const char *e = getenv(name);
+  return (e && atof(e) > 0) ? atof(e) : dflt;
+}
+
 double stage_cost(int d, const int mo_in[3], const int ld_in[3], const int mo_out[3], const int ld_out[3]) {
+  const double c_rowrow = env_cost("P3DFFT_B200_COST_ROWROW", 1.30), c_tload = env_cost("P3DFFT_B200_COST_TLOAD", 1.12);
   int fi = lead_dim(mo_in, ld_in), fo = lead_dim(mo_out, ld_out);
   double c;
   if (fi == d && fo == d) c = 1.00;
-  else if (fi == fo) c = 1.30;  // row-granular loads AND stores (measured slowest: 128-byte bulk copies per row)
+  else if (fi == fo) c = c_rowrow;  // row-granular loads AND stores (measured slowest: 128-byte bulk copies per row)
   else if (fi == d) {
     c = 1.08;  // contiguous (TMA-prefetched) loads + transposed stores: stores do not stall the pipeline
     // the stores of a tile are one short run per output index k: keep consecutive k close in memory (d second in the
@@ -106,7 +113,14 @@ double stage_cost(int d, const int mo_in[3], const int ld_in[3], const int mo_ou
       if (e != d && ld_out[e] > 1 && mo_out[e] < mo_out[d]) before++;
     if (before >= 2) c += 0.05;
   }
-  else if (fo == d) c = 1.12;  // transposed loads + contiguous stores
+  else if (fo == d) {
+    c = c_tload;  // transposed loads (TMA tensor boxes: one short row per input index) + contiguous stores
+    // the mirror image of the rule above: consecutive input indices close in memory (d second in the input order)
+    int before = 0;
+    for (int e = 0; e < 3; e++)
+      if (e != d && ld_in[e] > 1 && mo_in[e] < mo_in[d]) before++;
+    if (before >= 2) c += 0.05;
+  }
   else c = 1.60;
   if (mo_in[0] == mo_out[0] && mo_in[1] == mo_out[1] && mo_in[2] == mo_out[2]) c -= 0.02;
   return c;

@@ -58,6 +58,8 @@ def main():
             assert any(s.get("triple") for s in desc["stages"]), ("no L-X-Z triple planned", desc)
         if os.environ.get("P3DFFT_TEST_EXPECT_SYNC") and c.get("expect_sync", True):  # persistent pair kernels with tile-group flags
             assert any(s["pair_sync"] for s in desc["stages"]), ("pair without the tile-group form", desc)
+        if c.get("expect_variant"):  # some stage runs the named kernel variant
+            assert any(s["variant"].startswith(c["expect_variant"]) for s in desc["stages"]), (c["expect_variant"], [s["variant"] for s in desc["stages"]])
         og1 = orc.OGrid(g1d, c["dmap1"], c["mo1"], pd, rank, c.get("cs1", -1))
         og2 = orc.OGrid(g2d, c["dmap2"], c["mo2"], pd, rank, c.get("cs2", -1))
         assert list(g1.contents.Ldims) == og1.Ldims and list(g1.contents.GlobStart) == og1.GlobStart

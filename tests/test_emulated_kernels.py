@@ -6,7 +6,7 @@ library is exercised by tests/test_gpu_parity.py (-m gpu)."""
 import numpy as np
 import pytest
 
-from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, FASTCORE_CASES, PERMS, R2R_KINDS, RCC, RCC_S, half
+from cases import CCC, CCC_B, CCC_S, CCR, CCR_S, FASTCORE_CASES, PERMS, R2R_KINDS, RCC, RCC_S, TLOAD_CASES, half
 from util import TOL, check_golden, check_golden_kernels, run_1d, run_3d
 
 
@@ -304,3 +304,30 @@ def test_reference_golden_vectors_at_kernel_sizes_emulated(emu, orc):
     names = ["k_fwd_128x64x64", "k_fwd_768x6x4", "k_t1d_CFFT_FORWARD_D_768_d0_012_120", "k_t1d_DCT1_COMPLEX_D_513_d0_012_012",
              "k_t1d_DCT2_REAL_D_512_d0_012_120", "k_t1d_DST1_COMPLEX_D_255_d0_012_012", "k_c4_dct_deriv0_64x16x129"]
     assert check_golden_kernels(emu, orc, names, rank=0, world=1) == len(names)
+
+
+@pytest.mark.parametrize("case", TLOAD_CASES, ids=lambda c: "%s-%s-d%d" % ("x".join(map(str, c[0])), c[1], c[2]))
+def test_tensor_load_kernel(emu, orc, case):
+    """pow2_tload.cuh: power-of-two stages whose input is unit-stride along another dimension than the transform's (the
+    emulation restates the TMA tensor copy as a box gather with zero fill: it pins the tile / box / coordinate arithmetic)"""
+    g, t, dim, mo1, mo2, want = case
+    assert run_1d(emu, orc, g, t, dim, mo1, mo2, expect_variant=want) < TOL[4 if t.endswith("_S") else 8]
+
+
+def test_tensor_load_kernel_in_3d_and_switch(emu, orc, monkeypatch):
+    """the tensor-load kernel as the first stage of a 3D transform of a user array in a non-default storage order (with the
+    fused derivative), and P3DFFT_B200_NO_TLOAD=1 (the plain-load kernel it replaces)"""
+    n = (128, 24, 64)  # the real-to-complex dimension goes first whatever its stride
+    for mo1 in ((1, 0, 2), (2, 1, 0), (1, 2, 0), (2, 0, 1)):
+        for mo2 in ((0, 1, 2), (1, 2, 0)):
+            err, _, _, desc = run_3d(emu, orc, n, half(n), RCC, mo1, mo2, cs2=0, return_all=True)
+            assert desc["stages"][0]["variant"].startswith("tload<"), desc["stages"][0]["variant"]
+            assert err < TOL[8]
+    err, _, _, desc = run_3d(emu, orc, n, half(n), RCC, (1, 0, 2), (1, 2, 0), cs2=0, deriv=0, return_all=True)
+    assert desc["stages"][0]["variant"].startswith("tload<"), desc["stages"][0]["variant"]
+    assert err < TOL[8]
+    assert run_3d(emu, orc, n, half(n), RCC_S, (2, 1, 0), (1, 2, 0), cs2=0) < TOL[4]
+    monkeypatch.setenv("P3DFFT_B200_NO_TLOAD", "1")
+    err, _, _, desc = run_3d(emu, orc, n, half(n), RCC, (1, 0, 2), (0, 1, 2), cs2=0, return_all=True)
+    assert desc["stages"][0]["variant"].startswith("pow2<"), desc["stages"][0]["variant"]
+    assert err < TOL[8]

@@ -5,7 +5,7 @@ pure permutations must be bit-exact."""
 import numpy as np
 import pytest
 
-from cases import FASTCORE_CASES, CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, half
+from cases import FASTCORE_CASES, CCC, CCC_B, CCC_S, CCR, CCR_S, PERMS, R2R_KINDS, RCC, RCC_S, TLOAD_CASES, half
 from util import TOL, check_golden, check_golden_kernels, run_1d, run_3d
 
 pytestmark = pytest.mark.gpu
@@ -332,3 +332,52 @@ def test_reference_golden_vectors_at_kernel_sizes(gpu, orc):
     """the single-rank kernel-size golden cases (tests/golden/reference_golden_kernels.npz: outputs of the reference's own host
     code at M >= 64): the TMA-fed power-of-two, r2r and mixed-radix kernels pinned to the reference, not only to the oracle"""
     assert check_golden_kernels(gpu, orc, None, rank=0, world=1) >= 38
+
+
+@pytest.mark.parametrize("case", TLOAD_CASES, ids=lambda c: "%s-%s-d%d" % ("x".join(map(str, c[0])), c[1], c[2]))
+def test_tensor_load_kernel(gpu, orc, case):
+    """pow2_tload.cuh on hardware: TMA tensor copies (cp.async.bulk.tensor, 2-D boxes of a 3-D tensor map) feed power-of-two
+    stages whose input is unit-stride along another dimension than the transform's; zero-filled partial tiles"""
+    g, t, dim, mo1, mo2, want = case
+    assert run_1d(gpu, orc, g, t, dim, mo1, mo2, expect_variant=want) < TOL[4 if t.endswith("_S") else 8]
+
+
+def test_tensor_load_kernel_3d_orders_and_fallback(gpu, orc, monkeypatch):
+    """user arrays of 256 x 96 x 64 stored with y or z fastest: the R2C first stage takes the tensor-load kernel for every
+    such order (many tiles per CTA: the prefetch of the next tile and the barrier phases), also with the fused derivative and
+    in single precision; a device pointer that is not 16-byte aligned takes the plain-load kernel; P3DFFT_B200_NO_TLOAD=1"""
+    n = (256, 96, 64)
+    for mo1 in ((1, 0, 2), (2, 1, 0), (1, 2, 0), (2, 0, 1)):
+        for mo2 in ((0, 1, 2), (1, 2, 0), (2, 1, 0)):
+            err, _, _, desc = run_3d(gpu, orc, n, half(n), RCC, mo1, mo2, cs2=0, return_all=True)
+            assert desc["stages"][0]["variant"].startswith("tload<"), desc["stages"][0]["variant"]
+            assert err < TOL[8], (mo1, mo2, err)
+    assert run_3d(gpu, orc, n, half(n), RCC, (1, 0, 2), (1, 2, 0), cs2=0, deriv=0) < TOL[8]
+    assert run_3d(gpu, orc, n, half(n), RCC_S, (2, 1, 0), (1, 2, 0), cs2=0) < TOL[4]
+    # device pointers: aligned -> tensor maps on the user's own array; offset by 8 bytes -> the plain-load fallback
+    torch = pytest.importorskip("torch")
+    pg = gpu.init_proc_grid([1, 1, 1])
+    g1 = gpu.init_data_grid(n, -1, pg, [0, 1, 2], [1, 0, 2])
+    g2 = gpu.init_data_grid(half(n), 0, pg, [0, 1, 2], [1, 2, 0])
+    plan = gpu.plan_3Dtrans(g1, g2, gpu.init_3Dtype(RCC))
+    og1 = orc.OGrid(n, [0, 1, 2], [1, 0, 2], [1, 1, 1], 0)
+    og2 = orc.OGrid(half(n), [0, 1, 2], [1, 2, 0], [1, 1, 1], 0, 0)
+    G = orc.random_field(n, complex_=False, key=99)
+    a = np.ascontiguousarray(orc.local_of(G, og1), dtype=np.float64).ravel()
+    want = orc.local_of(orc.transform_global(G, RCC, half(n)), og2)
+    buf = torch.zeros(a.size + 2, device="cuda", dtype=torch.float64)
+    outs = []
+    for off in (0, 1):  # element offsets: 0 = 16-byte aligned (cudaMalloc), 1 = 8 bytes past it
+        buf[off:off + a.size] = torch.from_numpy(a).cuda()
+        X = torch.empty(want.size, device="cuda", dtype=torch.complex128)
+        gpu.exec_3Dtrans(plan, buf[off:off + a.size], X, 0)
+        gpu.sync()
+        outs.append(X.cpu().numpy().reshape(want.shape))
+        assert orc.rel_l2(outs[-1], want) < TOL[8], off
+    del buf, X
+    gpu.free_data_grid(g1)
+    gpu.free_data_grid(g2)
+    monkeypatch.setenv("P3DFFT_B200_NO_TLOAD", "1")
+    err, _, _, desc = run_3d(gpu, orc, n, half(n), RCC, (1, 0, 2), (0, 1, 2), cs2=0, return_all=True)
+    assert desc["stages"][0]["variant"].startswith("pow2<"), desc["stages"][0]["variant"]
+    assert err < TOL[8]

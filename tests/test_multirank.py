@@ -153,6 +153,17 @@ def test_other_distributions_and_empty_types():
     launch(4, cs)
 
 
+def test_tensor_load_first_stage_multirank():
+    """user arrays stored with y or z fastest: the first stage (R2C along the strided x) runs the tensor-load kernel
+    (pow2_tload.cuh) -- as a plain stage, as the exchange stage of a pencil grid and as a member of chunked pairs"""
+    n = (128, 64, 16)
+    T = dict(expect_variant="tload<", reps=1)
+    launch(2, [fwd(n, [1, 1, 2], mo1=[1, 0, 2], **T), fwd(n, [1, 1, 2], mo1=[2, 1, 0], deriv=1, **T), fwd(n, [1, 2, 1], mo1=[1, 2, 0], **T)],
+           timeout=1500)
+    launch(2, [fwd(n, [1, 1, 2], mo1=[1, 0, 2], **T)], timeout=1500, env_extra={"P3DFFT_B200_OVERLAP_ALIGN": "1", "P3DFFT_B200_OVERLAP_CHUNKS": "2"})
+    launch(4, [fwd(n, [1, 2, 2], mo1=[2, 0, 1], **T)], timeout=1500)
+
+
 FORCE_PAIRS = {"P3DFFT_B200_OVERLAP_ALIGN": "1", "P3DFFT_B200_OVERLAP_CHUNKS": "3", "P3DFFT_TEST_EXPECT_PAIRS": "1"}
 
 

@@ -14,15 +14,21 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 
-def run(lib, name, gd1, gd2, types, mo1, mo2, single, cs2=-1, deriv=-1, reps=5):
+def run(lib, name, gd1, gd2, types, mo1, mo2, single, cs2=-1, deriv=-1, reps=5, env=None):
     if ONLY and ONLY not in name:
         return
+    if not ONLY and name.startswith("TLOAD"):  # the strided-input shapes run only when asked for
+        return
+    for k, v in (env or {}).items():  # kernel-ladder switches are read when the plan is created
+        os.environ[k] = v
     pg = lib.init_proc_grid([1, 1, 1])
     g1 = lib.init_data_grid(gd1, -1, pg, [0, 1, 2], list(mo1))
     g2 = lib.init_data_grid(gd2, cs2, pg, [0, 1, 2], list(mo2))
     plan = lib.plan_3Dtrans(g1, g2, lib.init_3Dtype(types))
     desc = lib.describe_plan3d(plan)
     assert desc["ok"], desc
+    for k in (env or {}):
+        del os.environ[k]
     rdt = torch.float32 if single else torch.float64
     n1 = int(np.prod(gd1)) * desc["dt_in"]
     n2 = int(np.prod(gd2)) * desc["dt_out"]
@@ -86,6 +92,33 @@ def main():
     n = (2048, 2048, 64)
     run(lib, "C5 shape 2048x2048x64 R2C single (x,y stages at 2048 points)", n, (1025, 2048, 64), ["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"],
         (0, 1, 2), (1, 2, 0), True, cs2=0)
+    # user arrays stored with y fastest: the first stage reads x with a stride -- tensor-load kernel vs the plain-load kernel
+    n = (1024, 1024, 1024)
+    EC, ES = "EMPTY_TYPE_DOUBLE_COMPLEX", "EMPTY_TYPE_SINGLE_COMPLEX"
+    for tag, env in (("tensor loads", None), ("plain loads", {"P3DFFT_B200_NO_TLOAD": "1"})):
+        run(lib, f"TLOAD 1024^3 R2C double mo 102->120, {tag}", n, (513, 1024, 1024), ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], (1, 0, 2),
+            (1, 2, 0), False, cs2=0, env=env, reps=3)
+        run(lib, f"TLOAD 1024x1024x512 C2C(y) double mo 012->012 (transposed stores), {tag}", (1024, 1024, 512), (1024, 1024, 512),
+            [EC, "CFFT_FORWARD_D", EC], (0, 1, 2), (0, 1, 2), False, env=env, reps=3)
+        run(lib, f"TLOAD 1024x1024x512 C2C(y) double mo 012->102 (contiguous stores), {tag}", (1024, 1024, 512), (1024, 1024, 512),
+            [EC, "CFFT_FORWARD_D", EC], (0, 1, 2), (1, 0, 2), False, env=env, reps=3)
+        run(lib, f"TLOAD 1024^3 R2C single mo 102->120, {tag}", n, (513, 1024, 1024), ["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"], (1, 0, 2),
+            (1, 2, 0), True, cs2=0, env=env, reps=3)
+        run(lib, f"TLOAD 512^3 C2C(z) single mo 012->012, {tag}", (512, 512, 512), (512, 512, 512), [ES, ES, "CFFT_BACKWARD_S"], (0, 1, 2),
+            (0, 1, 2), True, env=env, reps=3)
+    # layout-search A/B (planner.cpp:stage_cost): a row-granular first stage followed by contiguous loads instead of a chain of
+    # tensor-load stages; and the headline forward transform with the transposition moved to the load side of stages 2 and 3
+    R = ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"]
+    RS = ["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"]
+    n = (1024, 1024, 1024)
+    run(lib, "TLOAD 1024^3 R2C double mo 102->120, row-row first stage", n, (513, 1024, 1024), R, (1, 0, 2), (1, 2, 0), False, cs2=0,
+        env={"P3DFFT_B200_COST_ROWROW": "1.0"}, reps=3)
+    run(lib, "TLOAD 1024^3 R2C double mo 012->120 (headline forward), default plan", n, (513, 1024, 1024), R, (0, 1, 2), (1, 2, 0), False, cs2=0, reps=3)
+    run(lib, "TLOAD 1024^3 R2C double mo 012->120 (headline forward), load-side transposition", n, (513, 1024, 1024), R, (0, 1, 2), (1, 2, 0), False,
+        cs2=0, env={"P3DFFT_B200_COST_TLOAD": "1.0"}, reps=3)
+    run(lib, "TLOAD 1024^3 R2C single mo 012->120, default plan", n, (513, 1024, 1024), RS, (0, 1, 2), (1, 2, 0), True, cs2=0, reps=3)
+    run(lib, "TLOAD 1024^3 R2C single mo 012->120, load-side transposition", n, (513, 1024, 1024), RS, (0, 1, 2), (1, 2, 0), True, cs2=0,
+        env={"P3DFFT_B200_COST_TLOAD": "1.0"}, reps=3)
     n = (256, 256, 256)
     run(lib, "256^3 R2C double", n, (129, 256, 256), ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], (0, 1, 2), (1, 2, 0), False, cs2=0, reps=20)
     n = (128, 128, 128)
