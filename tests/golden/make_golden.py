@@ -122,6 +122,14 @@ def large_cases():
            fwd("k_fwd_128x64x64_2x2", n, [1, 2, 2]), bwd("k_bwd_128x64x64_2x2", n, [1, 2, 2]),
            fwd("k_fwd_128x64x64_slab4", n, [1, 1, 4]), fwd("k_fwd_deriv1_128x64x64_slab2", n, [1, 1, 2], idir=1),
            fwd("k_fwd_single_128x64x64", n, [1, 1, 1], types=["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"])]
+    # user arrays stored with y or z fastest (test3D_r2c_memord.c's matrix at kernel size): the strided first stage takes the
+    # tensor-load kernel (pow2_tload.cuh); 1 rank and 2x2
+    for mo1 in ([1, 0, 2], [2, 1, 0], [1, 2, 0], [2, 0, 1]):
+        tag = "".join(map(str, mo1))
+        cs.append(fwd(f"k_fwd_128x64x64_mo{tag}", n, [1, 1, 1], mo1=mo1))
+    cs.append(fwd("k_fwd_128x64x64_mo102_2x2", n, [1, 2, 2], mo1=[1, 0, 2]))
+    cs.append(fwd("k_fwd_single_128x64x64_mo210", n, [1, 1, 1], types=["R2CFFT_S", "CFFT_FORWARD_S", "CFFT_FORWARD_S"], mo1=[2, 1, 0]))
+    cs.append(fwd("k_fwd_deriv0_128x64x64_mo120", n, [1, 1, 1], mo1=[1, 2, 0], idir=0))
     cs.append(fwd("k_fwd_2048x4x3", (2048, 4, 3), [1, 1, 1]))   # 1024-point complex core with the symmetric last pass
     cs.append(bwd("k_bwd_2048x4x3", (2048, 4, 3), [1, 1, 1]))
     cs.append(fwd("k_fwd_768x6x4", (768, 6, 4), [1, 1, 1]))     # mixed radix: 768-point real = 3 x 128 core
@@ -141,6 +149,13 @@ def large_cases():
             tag = f"{ty}_{g[dim]}_d{dim}_" + "".join(map(str, mo1)) + "_" + "".join(map(str, mo2))
             cs.append(dict(name=f"k_t1d_{tag}", mode="1d", types=[ty], dim=dim, procdims=[1, 1, 1], gdims1=list(g), gdims2=g2, cs1=-1,
                            cs2=dim if kind == "r2c" else -1, idir=-1, dmap1=[0, 1, 2], mo1=mo1, dmap2=[0, 1, 2], mo2=mo2))
+    for ty, g, dim, mo1, mo2 in (("CFFT_FORWARD_D", (8, 256, 6), 1, [0, 1, 2], [1, 0, 2]), ("CFFT_BACKWARD_D", (6, 4, 1024), 2, [0, 1, 2], [2, 1, 0]),
+                                 ("R2CFFT_D", (512, 16, 3), 0, [1, 0, 2], [0, 1, 2]), ("CFFT_FORWARD_S", (512, 16, 2), 0, [2, 0, 1], [0, 1, 2])):
+        kind = orc.type_info(ty)[0]
+        g2 = half(g, dim) if kind == "r2c" else list(g)
+        tag = f"{ty}_{g[dim]}_d{dim}_" + "".join(map(str, mo1)) + "_" + "".join(map(str, mo2))
+        cs.append(dict(name=f"k_t1d_strided_{tag}", mode="1d", types=[ty], dim=dim, procdims=[1, 1, 1], gdims1=list(g), gdims2=g2, cs1=-1,
+                       cs2=dim if kind == "r2c" else -1, idir=-1, dmap1=[0, 1, 2], mo1=mo1, dmap2=[0, 1, 2], mo2=mo2))
     return cs
 
 

@@ -300,8 +300,9 @@ def test_smooth_lengths_on_mixed_radix_kernel(emu, orc, q, mc, monkeypatch):
 
 def test_reference_golden_vectors_at_kernel_sizes_emulated(emu, orc):
     """a subset of the kernel-size golden cases on the emulation (the whole set runs on the GPU): 128 x 64 x 64 forward,
-    mixed-radix 768, DCT-I of 513 points, run-time r2r kinds"""
-    names = ["k_fwd_128x64x64", "k_fwd_768x6x4", "k_t1d_CFFT_FORWARD_D_768_d0_012_120", "k_t1d_DCT1_COMPLEX_D_513_d0_012_012",
+    mixed-radix 768, DCT-I of 513 points, run-time r2r kinds, user arrays stored with y or z fastest (tensor-load kernel)"""
+    names = ["k_fwd_128x64x64", "k_fwd_128x64x64_mo102", "k_fwd_128x64x64_mo210", "k_fwd_deriv0_128x64x64_mo120", "k_fwd_single_128x64x64_mo210",
+             "k_t1d_strided_CFFT_BACKWARD_D_1024_d2_012_210", "k_t1d_strided_R2CFFT_D_512_d0_102_012", "k_fwd_768x6x4", "k_t1d_CFFT_FORWARD_D_768_d0_012_120", "k_t1d_DCT1_COMPLEX_D_513_d0_012_012",
              "k_t1d_DCT2_REAL_D_512_d0_012_120", "k_t1d_DST1_COMPLEX_D_255_d0_012_012", "k_c4_dct_deriv0_64x16x129"]
     assert check_golden_kernels(emu, orc, names, rank=0, world=1) == len(names)
 

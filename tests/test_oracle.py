@@ -56,11 +56,11 @@ def test_oracle_matches_reference_golden_vectors(gold, orc):
 
 
 def test_oracle_matches_reference_golden_vectors_at_kernel_sizes(orc):
-    """the 42 kernel-size cases (128 x 64 x 64 on 1 / 2 / 4 ranks, 512...4096-point stages, 768 / 640 / 896 / 1536-point
+    """the 53 kernel-size cases (128 x 64 x 64 on 1 / 2 / 4 ranks, also stored with y or z fastest, 512...4096-point stages, 768 / 640 / 896 / 1536-point
     mixed-radix lengths, r2r kinds with 128...1024-point extensions): sampled elements + norms of the reference's outputs"""
     from util import compare_with_kernel_golden, golden_kernels
     index, z, mg = golden_kernels()
-    assert len(index) == 42 and [c["name"] for c in mg.large_cases()] == index, "index_kernels.json is stale: rerun make_golden.py"
+    assert len(index) == 53 and [c["name"] for c in mg.large_cases()] == index, "index_kernels.json is stale: rerun make_golden.py"
     for name in index:
         c = golden_case(z, name)
         pd = c["procdims"]
