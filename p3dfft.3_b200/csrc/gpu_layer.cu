@@ -524,16 +524,16 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   } else if (pow2_supported(d)) {
     M = real ? d.nfft / 2 : d.nfft;
   } else {
-    // smooth lengths: one odd factor 3, 5 or 7 times a power of two 128...1024 (mixed_pipe.cuh)
+    // smooth lengths: one odd factor 3, 5, 7, 9 or 15 times a power of two 64...1024 (mixed_pipe.cuh)
     if (d.kind < P3DFFTCU_K_C2C_FWD || d.kind > P3DFFTCU_K_C2R) return -1;
     if (real && (d.nfft % 2 || (d.kind == P3DFFTCU_K_C2R && d.nseg != 1))) return -1;
     M = real ? d.nfft / 2 : d.nfft;
     const char *nomix = getenv("P3DFFT_B200_NO_MIXED");
     if (nomix && atoi(nomix)) return -1;
-    for (int q : {3, 5, 7})
+    for (int q : {3, 5, 7, 9, 15})
       if (M % q == 0) {
         const int mc = M / q;
-        if (mc >= 128 && mc <= 1024 && (mc & (mc - 1)) == 0) { mixQ = q; mixMC = mc; }
+        if (mc >= 64 && mc <= 1024 && (mc & (mc - 1)) == 0) { mixQ = q; mixMC = mc; }
       }
     if (!mixQ) return -1;
   }
@@ -557,7 +557,7 @@ int pipe_setup(const p3dfftcu_stage_desc &d, PipePlan *pp, std::string *name) {
   pp->bytes = (int)copy_bytes;
   const int ts = fout != 0;
   const size_t csz = (size_t)d.prec * (r2r ? d.dt_out : 2);  // element size of the output runs
-  const int E = mixQ ? 16 : pow2_values_per_thread(M), TP = M / E;
+  const int E = mixQ ? mixed_values_per_thread(mixMC) : pow2_values_per_thread(M), TP = M / E;
   // transposed stores: runs of 128 bytes across the tile's pencils; contiguous stores: 256 threads per CTA
   // (single precision, local stages: 8 pencils = 64-byte runs with twice the CTAs per SM measured 4-14 % faster than 16
   //  pencils; exchange stages keep 128-byte runs where the tile fits: peer stores of 64-byte runs reach 580 instead of

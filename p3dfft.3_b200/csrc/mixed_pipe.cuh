@@ -1,5 +1,6 @@
-// mixed_pipe.cuh -- TMA-fed stage kernel for smooth lengths M = Q * MC: one odd factor Q in {3, 5, 7} times a power of two
-// MC in {128 ... 1024} (768 = 3 * 256, 640 = 5 * 128, 1536 = 3 * 512, 896 = 7 * 128, ...; real transforms of twice those).
+// mixed_pipe.cuh -- TMA-fed stage kernel for smooth lengths M = Q * MC: one odd factor Q in {3, 5, 7, 9, 15} times a power of two
+// MC in {64 ... 1024} (192 = 3 * 64, 768 = 3 * 256, 640 = 5 * 128, 1536 = 3 * 512, 896 = 7 * 128, 1152 = 9 * 128, 1920 = 15 * 128, ...; real
+// transforms of twice those), wherever Q * MC / 16 threads per pencil make whole warps within one CTA.
 //
 // Cooley-Tukey split n = MC n1 + n2, k = k1 + Q k2:
 //     X[k1 + Q k2] = sum_{n2} w_MC^{n2 k2} { w_M^{n2 k1} sum_{n1} x[MC n1 + n2] w_Q^{n1 k1} }
@@ -30,7 +31,7 @@ template <typename T, int MC, int Q, int KIND, int P, int TS> struct MixCfg {
   static constexpr size_t csz = 2 * sizeof(T);
   static constexpr size_t bar_bytes = 128;
   static constexpr size_t smem = bar_bytes + ((size_t)P * PITCH + T2N + T3N) * csz;
-  static constexpr bool valid = (E == 16) && (THREADS % 32 == 0) && (THREADS >= 64) && (THREADS <= 768) && (P <= 16) &&
+  static constexpr bool valid = (E == 16 || MC == 64) && (THREADS % 32 == 0) && (THREADS >= 64) && (THREADS <= 768) && (P <= 16) &&
                                 (smem <= kPipeSmemMax) && (TS ? P >= 2 : true) && (sizeof(T) == 8 ? THREADS <= 512 : true);
   // small CTAs (3 x 128 cores: 24 threads per pencil) share an SM in pairs: two independent CTAs overlap their phases
   enum { MINB = THREADS <= 256 ? 2 : 1 };
@@ -257,6 +258,7 @@ template <typename T, int MC, int Q, int KIND, int TS> const PipeInfo *mixed_inf
 
 template <typename T, int Q, int KIND, int TS> const PipeInfo *mixed_info_mc(int MC, int P) {
   switch (MC) {
+    case 64: return mixed_info_p<T, 64, Q, KIND, TS>(P);  // 8 values per thread (192 = 3 * 64, 320, 448, 576, 960)
     case 128: return mixed_info_p<T, 128, Q, KIND, TS>(P);
     case 256: return mixed_info_p<T, 256, Q, KIND, TS>(P);
     case 512: return mixed_info_p<T, 512, Q, KIND, TS>(P);
@@ -270,12 +272,14 @@ template <typename T, int KIND, int TS> const PipeInfo *mixed_info(int Q, int MC
     case 3: return mixed_info_mc<T, 3, KIND, TS>(MC, P);
     case 5: return mixed_info_mc<T, 5, KIND, TS>(MC, P);
     case 7: return mixed_info_mc<T, 7, KIND, TS>(MC, P);
+    case 9: return mixed_info_mc<T, 9, KIND, TS>(MC, P);    // 1152 = 9 * 128, 2304, 4608: the same radix-Q step, Q need not be prime
+    case 15: return mixed_info_mc<T, 15, KIND, TS>(MC, P);  // 1920 = 15 * 128, 3840
   }
   return nullptr;
 }
 
-// values per thread of the MC-point core are 16 for every MC served here; threads per pencil = Q * MC / 16
-inline int mixed_threads_per_pencil(int Q, int MC) { return Q * MC / 16; }
+// values per thread of the MC-point core: 16, or 8 for the 64-point core
+inline int mixed_values_per_thread(int MC) { return MC == 64 ? 8 : 16; }
 
 // defined in mixed_pipe_inst.cu, compiled once per (precision, kind)
 const PipeInfo *mixed_lookup(int prec, int kind, int ts, int Q, int MC, int P);

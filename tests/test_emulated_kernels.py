@@ -271,9 +271,9 @@ def test_reference_golden_vectors_single_rank(emu, orc):
     assert check_golden(emu, orc, None, rank=0, world=1) >= 100
 
 
-@pytest.mark.parametrize("q,mc", [(3, 128), (5, 128), (7, 128), (3, 256), (3, 512)])
+@pytest.mark.parametrize("q,mc", [(3, 128), (5, 128), (7, 128), (3, 256), (3, 512), (9, 128), (15, 128), (9, 256), (3, 64), (5, 64), (7, 64), (9, 64), (15, 64)])
 def test_smooth_lengths_on_mixed_radix_kernel(emu, orc, q, mc, monkeypatch):
-    """lengths M = q * 2^k (q = 3, 5, 7) on the TMA-fed mixed-radix kernel (mixed_pipe.cuh): C2C forward / backward, R2C / C2R of
+    """lengths M = q * 2^k (q = 3, 5, 7, 9, 15) on the TMA-fed mixed-radix kernel (mixed_pipe.cuh): C2C forward / backward, R2C / C2R of
     2M points, contiguous and transposed stores, partial tiles, double and single; then Bluestein (P3DFFT_B200_NO_MIXED=1)"""
     M = q * mc
     e2 = ["EMPTY_TYPE_DOUBLE_COMPLEX"] * 2

@@ -131,12 +131,12 @@ def test_r2r_kinds_on_pipe_kernel(gpu, orc, kind, L, monkeypatch):
     assert run_1d(gpu, orc, (n, 21, 3), f"{kind}_COMPLEX_D", 0, (0, 1, 2), (0, 1, 2), expect_variant="fastcore") < TOL[8]
 
 
-@pytest.mark.parametrize("M", [384, 640, 768, 896, 1280, 1536, 1792, 2560, 3072, 3584])
+@pytest.mark.parametrize("M", [384, 640, 768, 896, 1280, 1536, 1792, 2560, 3072, 3584, 1152, 1920, 2304, 192, 320, 448, 576, 960])
 def test_smooth_lengths_on_mixed_radix_kernel(gpu, orc, M, monkeypatch):
-    """lengths M = q * 2^k (q = 3, 5, 7; 2^k = 128...1024) on the TMA-fed mixed-radix kernel (mixed_pipe.cuh) instead of
+    """lengths M = q * 2^k (q = 3, 5, 7, 9, 15; 2^k = 64...1024) on the TMA-fed mixed-radix kernel (mixed_pipe.cuh) instead of
     Bluestein: C2C forward / backward, R2C / C2R of 2M points, contiguous and transposed stores, partial tiles, both precisions"""
     e2 = ["EMPTY_TYPE_DOUBLE_COMPLEX"] * 2
-    tag = [f",{q}x{M // q}>" for q in (3, 5, 7) if M % q == 0 and (M // q) & (M // q - 1) == 0]
+    tag = [f",{q}x{M // q}>" for q in (3, 5, 7, 9, 15) if M % q == 0 and (M // q) & (M // q - 1) == 0]
     for types, n, n2, kw in ((["CFFT_FORWARD_D"] + e2, (M, 21, 3), (M, 21, 3), {}),
                              (["CFFT_BACKWARD_D"] + e2, (M, 21, 3), (M, 21, 3), {}),
                              (["R2CFFT_D"] + e2, (2 * M, 21, 3), (M + 1, 21, 3), dict(cs2=0)),

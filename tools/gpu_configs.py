@@ -17,7 +17,7 @@ import __graft_entry__ as ge  # noqa: E402
 def run(lib, name, gd1, gd2, types, mo1, mo2, single, cs2=-1, deriv=-1, reps=5, env=None):
     if ONLY and ONLY not in name:
         return
-    if not ONLY and name.startswith("TLOAD"):  # the strided-input shapes run only when asked for
+    if not ONLY and (name.startswith("TLOAD") or name.startswith("SMOOTH")):  # A/B shapes run only when asked for
         return
     for k, v in (env or {}).items():  # kernel-ladder switches are read when the plan is created
         os.environ[k] = v
@@ -119,6 +119,14 @@ def main():
     run(lib, "TLOAD 1024^3 R2C single mo 012->120, default plan", n, (513, 1024, 1024), RS, (0, 1, 2), (1, 2, 0), True, cs2=0, reps=3)
     run(lib, "TLOAD 1024^3 R2C single mo 012->120, load-side transposition", n, (513, 1024, 1024), RS, (0, 1, 2), (1, 2, 0), True, cs2=0,
         env={"P3DFFT_B200_COST_TLOAD": "1.0"}, reps=3)
+    # smooth lengths added last in round 2: 9 x 2^k, 15 x 2^k and the 64-point cores (3 x 64 ...); Bluestein before
+    for tag, env in (("mixed-radix kernel", None), ("Bluestein", {"P3DFFT_B200_NO_MIXED": "1"})):
+        run(lib, f"SMOOTH 1152^3 R2C double (9 x 128 / 9 x 64 cores), {tag}", (1152, 1152, 1152), (577, 1152, 1152), R, (0, 1, 2), (1, 2, 0), False,
+            cs2=0, env=env, reps=2)
+        run(lib, f"SMOOTH 960^3 C2C double (15 x 64), {tag}", (960, 960, 960), (960, 960, 960), ["CFFT_FORWARD_D"] * 3, (0, 1, 2), (0, 1, 2), False,
+            env=env, reps=2)
+        run(lib, f"SMOOTH 192^3 R2C double (3 x 64 / 3 x 32...), {tag}", (192, 192, 192), (97, 192, 192), R, (0, 1, 2), (1, 2, 0), False, cs2=0,
+            env=env, reps=10)
     n = (256, 256, 256)
     run(lib, "256^3 R2C double", n, (129, 256, 256), ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], (0, 1, 2), (1, 2, 0), False, cs2=0, reps=20)
     n = (128, 128, 128)
