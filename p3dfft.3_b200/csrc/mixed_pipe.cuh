@@ -19,6 +19,75 @@
 
 namespace p3b {
 
+// ------------------------------------------------------------------ radix-Q butterfly (odd Q) in registers
+// cos / sin of 2 pi m / Q, m < Q, as compile-time constants (indices are constant after unrolling)
+template <int Q> struct QRoots;
+template <> struct QRoots<3> {
+  static __host__ __device__ constexpr double c(int m) { constexpr double t[3] = {1.0, -0.4999999999999998, -0.5000000000000004}; return t[m]; }
+  static __host__ __device__ constexpr double s(int m) { constexpr double t[3] = {0.0, 0.8660254037844387, -0.8660254037844384}; return t[m]; }
+};
+template <> struct QRoots<5> {
+  static __host__ __device__ constexpr double c(int m) { constexpr double t[5] = {1.0, 0.30901699437494745, -0.8090169943749473, -0.8090169943749476, 0.30901699437494723}; return t[m]; }
+  static __host__ __device__ constexpr double s(int m) { constexpr double t[5] = {0.0, 0.9510565162951535, 0.5877852522924732, -0.587785252292473, -0.9510565162951536}; return t[m]; }
+};
+template <> struct QRoots<7> {
+  static __host__ __device__ constexpr double c(int m) { constexpr double t[7] = {1.0, 0.6234898018587336, -0.22252093395631434, -0.900968867902419, -0.9009688679024191, -0.2225209339563146, 0.6234898018587334}; return t[m]; }
+  static __host__ __device__ constexpr double s(int m) { constexpr double t[7] = {0.0, 0.7818314824680298, 0.9749279121818236, 0.43388373911755823, -0.433883739117558, -0.9749279121818236, -0.7818314824680299}; return t[m]; }
+};
+template <> struct QRoots<9> {
+  static __host__ __device__ constexpr double c(int m) { constexpr double t[9] = {1.0, 0.766044443118978, 0.17364817766693041, -0.4999999999999998, -0.9396926207859083, -0.9396926207859084, -0.5000000000000004, 0.17364817766692997, 0.7660444431189778}; return t[m]; }
+  static __host__ __device__ constexpr double s(int m) { constexpr double t[9] = {0.0, 0.6427876096865393, 0.984807753012208, 0.8660254037844387, 0.3420201433256689, -0.34202014332566866, -0.8660254037844384, -0.9848077530122081, -0.6427876096865396}; return t[m]; }
+};
+template <> struct QRoots<15> {
+  static __host__ __device__ constexpr double c(int m) { constexpr double t[15] = {1.0, 0.9135454576426009, 0.6691306063588582, 0.30901699437494745, -0.10452846326765333, -0.4999999999999998, -0.8090169943749473, -0.9781476007338057, -0.9781476007338057, -0.8090169943749476, -0.5000000000000004, -0.10452846326765423, 0.30901699437494723, 0.6691306063588585, 0.913545457642601}; return t[m]; }
+  static __host__ __device__ constexpr double s(int m) { constexpr double t[15] = {0.0, 0.40673664307580015, 0.7431448254773941, 0.9510565162951535, 0.9945218953682734, 0.8660254037844387, 0.5877852522924732, 0.20791169081775931, -0.20791169081775907, -0.587785252292473, -0.8660254037844384, -0.9945218953682733, -0.9510565162951536, -0.743144825477394, -0.40673664307580015}; return t[m]; }
+};
+
+// The radix-Q step runs as register butterflies (one thread transforms the Q values x[MC n1 + n2], n1 < Q, of one n2 and
+// writes them back in place) for Q >= BflyMinQ<T>::value; below that every thread group evaluates its own output row by definition
+// from the whole pencil (Q - 1 complex multiplies per value: FP64-issue-bound from Q = 5 on).  Measured on B200, 1-GPU cubes
+// in double, by definition -> butterflies (profiles/r02v_mixab_*.txt): 768^3 R2C 5.12 -> 4.80 ms, 640^3 C2C 6.20 -> 5.48,
+// 896^3 19.1 -> 14.8, 1152^3 R2C 28.8 -> 21.3, 960^3 35.4 -> 23.0; single precision, Q = 3: 3.32 -> 3.34 (the 3 x 256
+// stages lose 4-10 %, the 3 x 128 stage gains 7 %), hence by definition there.  -DP3B_MIX_BFLY_MINQ_F64/_F32 override.
+#ifndef P3B_MIX_BFLY_MINQ_F64
+#define P3B_MIX_BFLY_MINQ_F64 3
+#endif
+#ifndef P3B_MIX_BFLY_MINQ_F32
+#define P3B_MIX_BFLY_MINQ_F32 5
+#endif
+template <typename T> struct BflyMinQ { enum { value = sizeof(T) == 8 ? P3B_MIX_BFLY_MINQ_F64 : P3B_MIX_BFLY_MINQ_F32 }; };
+
+// forward DFT of odd length Q by its real symmetry: a_j = x_j + x_{Q-j}, b_j = x_j - x_{Q-j} (j <= H = (Q-1)/2),
+//   y_k = x_0 + sum_j a_j cos(2 pi j k / Q) - i sum_j b_j sin(2 pi j k / Q),  y_{Q-k} = the same with + i:
+// (Q-1)^2 real multiply-adds instead of (Q-1)^2 complex multiplies.  emit(k, y_k) receives the outputs.
+template <typename T, int Q, typename Emit> __device__ __forceinline__ void dft_odd(const typename cx<T>::type *x, Emit emit) {
+  typedef typename cx<T>::type C;
+  constexpr int H = (Q - 1) / 2;
+  C a[H], b[H];
+  C y0 = x[0];
+#pragma unroll
+  for (int j = 1; j <= H; j++) {
+    a[j - 1] = cadd(x[j], x[Q - j]);
+    b[j - 1] = csub(x[j], x[Q - j]);
+    y0 = cadd(y0, a[j - 1]);
+  }
+  emit(0, y0);
+#pragma unroll
+  for (int k = 1; k <= H; k++) {
+    T cr = x[0].x, ci = x[0].y, dr = (T)0, di = (T)0;
+#pragma unroll
+    for (int j = 1; j <= H; j++) {
+      const T c = (T)QRoots<Q>::c((j * k) % Q), sn = (T)QRoots<Q>::s((j * k) % Q);
+      cr += c * a[j - 1].x;
+      ci += c * a[j - 1].y;
+      dr += sn * b[j - 1].x;
+      di += sn * b[j - 1].y;
+    }
+    emit(k, mk<T>(cr + di, ci - dr));      // c_k - i d_k
+    emit(Q - k, mk<T>(cr - di, ci + dr));  // c_k + i d_k
+  }
+}
+
 template <typename T, int MC, int Q, int KIND, int P, int TS> struct MixCfg {
   enum { E = Pow2Cfg<MC>::E, TPC = MC / E, TP = Q * TPC, THREADS = P * TP, M = Q * MC };
   enum { R1 = Pow2Cfg<MC>::R1, R2 = Pow2Cfg<MC>::R2, R3 = Pow2Cfg<MC>::R3 };
@@ -105,7 +174,13 @@ mixed_pipe_kernel(const __grid_constant__ StageParams S) {
     uo += puB;
     vo += pvB;
     const bool live = uo < S.nu && vo < S.nv;
-    mbar_wait(bar, parity);
+    if constexpr (Q >= BflyMinQ<T>::value) {
+      // the register butterflies below read every pencil of the tile: wait for all of them (one phase per pencil and tile)
+#pragma unroll 1
+      for (int p = 0; p < P; p++) mbar_wait(bars + p, parity);
+    } else {
+      mbar_wait(bar, parity);
+    }
     parity ^= 1;
 
     if constexpr (c2r) {
@@ -133,26 +208,47 @@ mixed_pipe_kernel(const __grid_constant__ StageParams S) {
       }
       __syncthreads();
     }
-    // ---------------- radix-Q step of group qA: v[m] = w_M^{n2 qA} sum_{n1} x[MC n1 + n2] w_Q^{n1 qA}, n2 = tcA + TPC m
+    // ---------------- radix-Q step: v[m] = w_M^{n2 qA} sum_{n1} x[MC n1 + n2] w_Q^{n1 qA}, n2 = tcA + TPC m, for group qA
     auto X = [&](int j) -> C {
       const C x = BA[j];
       return (bwd && !c2r) ? cconj(x) : x;
     };
     C v[E];
+    if constexpr (Q >= BflyMinQ<T>::value) {
+      // register butterflies: the P * MC butterflies of the tile are dealt to the CTA's threads (b = pencil * MC + n2); butterfly
+      // n2 reads x[MC n1 + n2], n1 < Q, and writes y[k1] w_M^{n2 k1} back to x[MC k1 + n2] -- locations no other butterfly
+      // touches; group k1 then finds its row contiguous at [MC k1, MC k1 + MC)
+#pragma unroll 1
+      for (int bf = tid; bf < P * MC; bf += THREADS) {
+        const int n2 = bf & (MC - 1);
+        C *Bp = B + (bf / MC) * PITCH;
+        C x[Q];
 #pragma unroll
-    for (int m = 0; m < E; m++) v[m] = X(tcA + TPC * m);
-#pragma unroll
-    for (int n1 = 1; n1 < Q; n1++) {
-      const C wq = __ldg(&tw[((n1 * qA) % Q) * MC * twscale]);  // w_Q^{n1 qA}
-#pragma unroll
-      for (int m = 0; m < E; m++) {
-        const C x = cmul(X(n1 * MC + tcA + TPC * m), wq);
-        v[m] = cadd(v[m], x);
+        for (int n1 = 0; n1 < Q; n1++) {
+          const C z = Bp[n1 * MC + n2];
+          x[n1] = (bwd && !c2r) ? cconj(z) : z;
+        }
+        dft_odd<T, Q>(x, [&](int k1, const C &y) { Bp[k1 * MC + n2] = k1 ? cmul(y, __ldg(&tw[n2 * k1 * twscale])) : y; });
       }
-    }
-    if (qA > 0) {
+      __syncthreads();
 #pragma unroll
-      for (int m = 0; m < E; m++) v[m] = cmul(v[m], __ldg(&tw[(tcA + TPC * m) * qA * twscale]));
+      for (int m = 0; m < E; m++) v[m] = BA[qA * MC + tcA + TPC * m];
+    } else {
+#pragma unroll
+      for (int m = 0; m < E; m++) v[m] = X(tcA + TPC * m);
+#pragma unroll
+      for (int n1 = 1; n1 < Q; n1++) {
+        const C wq = __ldg(&tw[((n1 * qA) % Q) * MC * twscale]);  // w_Q^{n1 qA}
+#pragma unroll
+        for (int m = 0; m < E; m++) {
+          const C x = cmul(X(n1 * MC + tcA + TPC * m), wq);
+          v[m] = cadd(v[m], x);
+        }
+      }
+      if (qA > 0) {
+#pragma unroll
+        for (int m = 0; m < E; m++) v[m] = cmul(v[m], __ldg(&tw[(tcA + TPC * m) * qA * twscale]));
+      }
     }
     __syncthreads();  // the pencil is in registers: its buffer now carries the exchanges of the Q cores
 

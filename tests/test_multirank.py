@@ -153,6 +153,14 @@ def test_other_distributions_and_empty_types():
     launch(4, cs)
 
 
+def test_smooth_lengths_with_exchange_segments():
+    """mixed-radix kernel (192 = 3 x 64, 640 = 5 x 128 points) as an exchange stage: its stores go through the per-peer segment
+    table; R2C of 384 points (192-point core) in front of an exchange"""
+    T = dict(reps=1)
+    launch(2, [c2c((192, 12, 8), [1, 2, 1], expect_variant="pipe<f64,M=192", **T), fwd((384, 12, 8), [1, 1, 2], expect_variant="pipe<f64,M=192", **T),
+               bwd((384, 12, 8), [1, 2, 1], **T), c2c((640, 4, 6), [1, 1, 2], expect_variant="pipe<f64,M=640", **T)], timeout=1500)
+
+
 def test_tensor_load_first_stage_multirank():
     """user arrays stored with y or z fastest: the first stage (R2C along the strided x) runs the tensor-load kernel
     (pow2_tload.cuh) -- as a plain stage, as the exchange stage of a pencil grid and as a member of chunked pairs"""

@@ -17,7 +17,7 @@ import __graft_entry__ as ge  # noqa: E402
 def run(lib, name, gd1, gd2, types, mo1, mo2, single, cs2=-1, deriv=-1, reps=5, env=None):
     if ONLY and ONLY not in name:
         return
-    if not ONLY and (name.startswith("TLOAD") or name.startswith("SMOOTH")):  # A/B shapes run only when asked for
+    if not ONLY and name.split(" ")[0] in ("TLOAD", "SMOOTH", "MIXAB"):  # A/B shapes run only when asked for
         return
     for k, v in (env or {}).items():  # kernel-ladder switches are read when the plan is created
         os.environ[k] = v
@@ -127,6 +127,15 @@ def main():
             env=env, reps=2)
         run(lib, f"SMOOTH 192^3 R2C double (3 x 64 / 3 x 32...), {tag}", (192, 192, 192), (97, 192, 192), R, (0, 1, 2), (1, 2, 0), False, cs2=0,
             env=env, reps=10)
+    # A/B of the mixed-radix kernel's radix-Q step (by definition vs register butterflies): run once per library build
+    C3 = ["CFFT_FORWARD_D"] * 3
+    run(lib, "MIXAB 768^3 R2C double (3 x 128, 3 x 256)", (768, 768, 768), (385, 768, 768), R, (0, 1, 2), (1, 2, 0), False, cs2=0, reps=3)
+    run(lib, "MIXAB 768^3 C2R double", (385, 768, 768), (768, 768, 768), ["C2RFFT_D", "CFFT_BACKWARD_D", "CFFT_BACKWARD_D"], (1, 2, 0), (0, 1, 2), False, reps=3)
+    run(lib, "MIXAB 640^3 C2C double (5 x 128)", (640, 640, 640), (640, 640, 640), C3, (0, 1, 2), (0, 1, 2), False, reps=3)
+    run(lib, "MIXAB 896^3 C2C double (7 x 128)", (896, 896, 896), (896, 896, 896), C3, (0, 1, 2), (0, 1, 2), False, reps=3)
+    run(lib, "MIXAB 1152^3 R2C double (9 x 64, 9 x 128)", (1152, 1152, 1152), (577, 1152, 1152), R, (0, 1, 2), (1, 2, 0), False, cs2=0, reps=3)
+    run(lib, "MIXAB 960^3 C2C double (15 x 64)", (960, 960, 960), (960, 960, 960), C3, (0, 1, 2), (0, 1, 2), False, reps=3)
+    run(lib, "MIXAB 768^3 R2C single", (768, 768, 768), (385, 768, 768), RS, (0, 1, 2), (1, 2, 0), True, cs2=0, reps=3)
     n = (256, 256, 256)
     run(lib, "256^3 R2C double", n, (129, 256, 256), ["R2CFFT_D", "CFFT_FORWARD_D", "CFFT_FORWARD_D"], (0, 1, 2), (1, 2, 0), False, cs2=0, reps=20)
     n = (128, 128, 128)
