@@ -71,6 +71,11 @@ module p3dfft_plus_plus
       import
       integer(C_INT) :: mygrid, ldims(3), glob_start(3), gdims(3), dim_conj_sym, pgrid, dmap(3), mem_order(3)
     end subroutine
+    ! (the reference module spells this interface with three f's, build/fp3dfft++mod.f90:87; kept so that callers compile unchanged)
+    subroutine p3dffft_inv_mo(mo, imo) bind(C, name='p3dfft_inv_mo')
+      import
+      integer(C_INT) :: mo(3), imo(3)
+    end subroutine
     subroutine p3dfft_plan_1Dtrans(plan, grid1, grid2, type_id, d) bind(C, name='p3dfft_plan_1Dtrans_f')
       import
       integer(C_INT) :: plan, grid1, grid2, type_id, d

@@ -4,10 +4,12 @@
 //
 // Cooley-Tukey split n = MC n1 + n2, k = k1 + Q k2:
 //     X[k1 + Q k2] = sum_{n2} w_MC^{n2 k2} { w_M^{n2 k1} sum_{n1} x[MC n1 + n2] w_Q^{n1 k1} }
-// A pencil is handled by Q groups of TPC = MC/16 threads.  Group k1 builds ITS row of the radix-Q step straight from the
-// pencil as it landed in shared memory (Q loads and Q-1 complex multiplies per value: the odd-radix butterfly is evaluated
-// by definition, shared between the groups only through shared memory -- Q is small and the stage is HBM-bound), applies the
-// twiddle w_M^{n2 k1}, and then runs the SAME register-resident MC-point core as the power-of-two kernel (pow2_pipe.cuh:
+// A pencil is handled by Q groups of TPC = MC/16 threads.  The radix-Q step (the braces) runs first, in one of two forms:
+// register butterflies -- a thread loads the Q values x[MC n1 + n2] of one n2, evaluates the odd-length DFT by its real
+// symmetry and writes the Q outputs, twiddled, back in place, so that group k1 finds its row contiguous (dft_odd below) --
+// or, the kernel's first form, kept where it measured faster (single precision, Q = 3): group k1 builds ITS row straight
+// from the pencil as it landed (Q loads and Q-1 complex multiplies per value, by definition).  Either way group k1 then
+// holds its row times the twiddle w_M^{n2 k1} and runs the SAME register-resident MC-point core as the power-of-two kernel (pow2_pipe.cuh:
 // radix-16 passes, padded in-place exchanges, smem twiddle tables) on its own sub-buffer.  Data movement is the power-of-two
 // kernel's: one bulk copy (cp.async.bulk + mbarrier) per pencil, issued for the NEXT tile as soon as the last exchange has
 // been read back; transposed stores re-map threads to lanes-across-pencils in that exchange.  Barriers are CTA-wide (a
