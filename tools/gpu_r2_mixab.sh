@@ -1,6 +1,9 @@
 #!/bin/bash
 # round 2, last seconds of box time: the mixed-radix kernel's radix-Q step as register butterflies (library build B,
-# p3dfft.3_b200/lib_b) against the by-definition form (build A, p3dfft.3_b200/lib) -- parity of B, then both timed
+# p3dfft.3_b200/lib_b) against the by-definition form (build A, p3dfft.3_b200/lib) -- parity of B, then both timed.
+# How the two builds were made (lib_b travels gzipped: the snapshot limit is 512 MiB):
+#   make -j LIBDIR=p3dfft.3_b200/lib_b EXTRA_NVFLAGS='-DP3B_MIX_BFLY_MINQ_F64=3 -DP3B_MIX_BFLY_MINQ_F32=3' && gzip -1 -k p3dfft.3_b200/lib_b/libp3dfft.3.so
+#   make -j EXTRA_NVFLAGS='-DP3B_MIX_BFLY_MINQ_F64=99 -DP3B_MIX_BFLY_MINQ_F32=99'
 TAG=${TAG:-r02v}
 mkdir -p gpurun_out
 T0=$(date +%s)
