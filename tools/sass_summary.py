@@ -21,6 +21,9 @@ PICK = [  # (object, mangled-name fragment, label)
     ("pipe_8_13.o", "pow2_pipe_kernelIdLi1024ELi13ELi4ELi0E", "pow2_pipe_kernel<double,1024,r2r run-time kind,4,contiguous>"),
     ("pipe_4_1.o", "pow2_pipe_kernelIfLi2048ELi1ELi8ELi1E", "pow2_pipe_kernel<float,2048,C2C fwd,8,transposed> config C5"),
     ("mixed_8_1.o", "mixed_pipe_kernelIdLi256ELi3ELi1ELi8ELi1E", "mixed_pipe_kernel<double,256,3,C2C fwd,8,transposed> 768 points"),
+    ("mixed_8_1.o", "mixed_pipe_kernelIdLi128ELi9ELi1ELi4ELi1E", "mixed_pipe_kernel<double,128,9,C2C fwd,4,transposed> 1152 points (register butterflies)"),
+    ("tload_8_1.o", "pow2_tload_kernelIdLi1024ELi1ELi8ELi0E", "pow2_tload_kernel<double,1024,C2C fwd,8,contiguous> strided input (TMA tensor-map loads)"),
+    ("tload_8_3.o", "pow2_tload_kernelIdLi512ELi3ELi16ELi0E", "pow2_tload_kernel<double,512,R2C,16,contiguous> strided real input"),
     ("fastcore_inst.o", "fastcore_stage_kernelIdLi2048ELi1E", "fastcore_stage_kernel<double,2048,bluestein>"),
 ]
 OPS = ["UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "DFMA", "DADD", "DMUL", "FFMA", "FADD", "FMUL", "BAR", "ATOM", "RED", "MEMBAR",
@@ -52,8 +55,9 @@ def main():
                             counts[o] += 1
                             break
         lines.append(f"{label} | {total} | " + " ".join(f"{o}:{counts[o]}" for o in OPS if counts[o]))
-    lines.append("(no HMMA / DMMA / IMMA / UTCMMA anywhere: no tensor-core instruction; no UTMALDG / UTMASTG: bulk copies are the "
-                 "non-tensor cp.async.bulk form, UBLKCP)")
+    lines.append("(no HMMA / DMMA / IMMA / UTCMMA anywhere: no tensor-core instruction; UBLKCP = cp.async.bulk, the whole-pencil copies of "
+                 "the unit-stride kernels; UTMALDG = cp.async.bulk.tensor, the tensor-map loads of pow2_tload_kernel for strided inputs; "
+                 "no UTMASTG: stores go from registers)")
     out = os.path.join(ROOT, "profiles", f"{tag}_sass_summary.txt")
     with open(out, "w") as f:
         f.write("\n".join(lines) + "\n")
