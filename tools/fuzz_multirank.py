@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""fuzz_multirank.py [seed] [batches] -- random multi-rank cases on the CPU emulation: random grids, processor grids on 2-4
+"""fuzz_multirank.py [seed] [batches] [big] -- random multi-rank cases on the CPU emulation: random grids, processor grids on 2-4
 ranks, memory orders, forward / backward / C2C, fused derivative, in-place, random chunking of the overlapped pairs; every
 rank checks its block against the oracle (tests/mp_worker.py).  Development tool; tests/test_multirank.py runs two batches."""
 import json,sys,subprocess,os,signal,random,itertools
@@ -7,10 +7,11 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from test_multirank import *
 rnd=random.Random(int(sys.argv[1]) if len(sys.argv)>1 else 1)
 perms=list(itertools.permutations((0,1,2)))
+BIG=[128,192,256,384] if len(sys.argv)>3 and sys.argv[3]=='big' else []  # kernel sizes: TMA-fed, tensor-load and mixed-radix kernels as exchange stages
 def rand_case(world):
     grids={2:[[1,1,2],[1,2,1]],3:[[1,1,3],[1,3,1]],4:[[1,1,4],[1,2,2],[1,4,1]]}[world]
     pd=rnd.choice(grids)
-    n=(rnd.choice([8,12,16,20,32,64]), rnd.randint(4,24), rnd.randint(4,24))
+    n=(rnd.choice([8,12,16,20,32,64]+BIG), rnd.randint(4,24), rnd.randint(4,24))
     kind=rnd.choice(["fwd","bwd","c2c"])
     kw={}
     if rnd.random()<0.5:
